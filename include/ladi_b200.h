@@ -1,0 +1,151 @@
+/* ladi_b200.h -- C ABI of libladi_b200.so: hand-written sm_100a kernels for the LaDI-VTON try-on hot path.
+ *
+ * The reference (miccunifi/ladi-vton) has no FFI of its own: it is pure Python and every GPU operation on its hot path is
+ * a PyTorch/cuDNN/cuBLAS library call made from `StableDiffusionTryOnePipeline.__call__`
+ * (/root/reference/src/vto_pipelines/tryon_pipe.py:494-765).  This header is the boundary a maintainer binds (ctypes, see
+ * INTEGRATION.md) to replace those library calls.  Each entry point names the reference call-site(s) it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are CALLER-OWNED DEVICE pointers (e.g. torch.Tensor.data_ptr());
+ *  - activations are NHWC bf16 (`pitch` = elements between consecutive pixels, multiple of 8 => 16-byte aligned rows);
+ *  - `stream` is a cudaStream_t passed as void*; nothing allocates, synchronises or uses an implicit stream, so every call
+ *    is CUDA-graph capturable;
+ *  - return 0 (LADI_OK) on success; otherwise an error code, with a thread-local message in ladi_last_error();
+ *    no exceptions/aborts cross the ABI;
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point returns LADI_ERR_CUDA.
+ */
+#ifndef LADI_B200_H
+#define LADI_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LADI_API __attribute__((visibility("default")))
+#else
+#define LADI_API
+#endif
+
+#define LADI_OK 0
+#define LADI_ERR_INVALID 1
+#define LADI_ERR_CUDA 2
+
+#define LADI_ACT_NONE 0
+#define LADI_ACT_SILU 1
+#define LADI_ACT_GEGLU 2
+
+LADI_API const char* ladi_last_error(void);
+LADI_API int ladi_abi_version(void);
+
+/* ---- implicit-GEMM convolution / GEMM (tcgen05 + TMA) --------------------------------------------------------------
+ * Replaces nn.Conv2d (3x3 s1 p1, 3x3 s2, 1x1) and nn.Linear of: diffusers ResnetBlock2D / Transformer2DModel /
+ * Downsample2D / Upsample2D inside UNet2DConditionModel.forward (call-site tryon_pipe.py:732), the VAE Encoder/Decoder
+ * (src/models/vae.py:99-119, 183-212; AutoencoderKL.py:151,163) and EMASC (src/models/emasc.py:25-40).
+ *
+ * out[n,y,x,:] = epilogue( sum_{tap,src,c} in_src[n, y*stride+ky-pad_lo, x*stride+kx-pad_lo, c] * W[:, k(tap,src,c)]
+ *                          + sum_{sc,c} sc[n,y,x,c] * W[:, k(sc,c)] )
+ * The sources are concatenated along channels (UNet skip `torch.cat([x, skip], 1)`, diffusers CrossAttnUpBlock2D) WITHOUT
+ * materialising the concat; the optional `sc` sources are the ResnetBlock2D 1x1 `conv_shortcut` folded into the same
+ * accumulation.  Weight layout: bf16 [c_out][k_total], K order = for tap(ky,kx) row-major: for src: channels padded to a
+ * multiple of 64 (zero weights in the padding); then for sc: channels padded to 64.  k_total = 64 * (#K blocks).
+ * A GEMM out[M,N] = A[M,K] W[N,K]^T is ksize=1, n=1, h_out=1, w_out=M, src_c=K.
+ * epilogue: +bias[c] (or +bias[row] if bias_per_row; bias += *step_ptr * bias_step_stride when step_ptr != NULL),
+ *           act (SiLU, or GEGLU on interleaved (value,gate) column pairs -> c_out/2 outputs), +residual, *row_scale[row]. */
+typedef struct ladi_conv_desc {
+  int n, h_out, w_out, c_out;
+  int h_in, w_in;            /* 0 => h_out*stride, w_out*stride */
+  int ksize, stride, pad_lo; /* ksize 1|3, stride 1|2, pad_lo = top/left padding (1; 0 for the VAE (0,1,0,1) downsample) */
+  int n_src;
+  const void* src[2];
+  int src_c[2];
+  int src_pitch[2];
+  int n_sc;
+  const void* sc[2];
+  int sc_c[2];
+  int sc_pitch[2];
+  const void* weight;
+  int k_total;
+  int weight_pitch;          /* elements between weight rows (>= k_total, multiple of 8) */
+  const float* bias;
+  int bias_per_row;
+  int bias_step_stride;
+  const int* step_ptr;
+  const void* residual;
+  int residual_pitch;
+  const float* row_scale;
+  int act;
+  void* out;
+  int out_pitch;
+  int out_fp32;
+  int force_bn;              /* 0 = auto; else N tile in {32,64,128,160,192,256} (tests / tuning) */
+} ladi_conv_desc;
+LADI_API int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream);
+
+/* ---- fused multi-head attention, head_dim 64 (flash-style: S and O live in TMEM, online softmax in exp2) ------------
+ * Replaces diffusers CrossAttention.forward for attn1 (self) and attn2 (cross, 77 text tokens) of every
+ * BasicTransformerBlock in the UNet (torch SDPA / xformers in the reference, src/inference.py:143-147).
+ * element (b, i, h, e) of q is q[b*q_batch_stride + i*q_pitch + h*64 + e]; same for k, v, out.  No mask. */
+typedef struct ladi_attn_desc {
+  int batch, heads, nq, nkv;
+  const void* q; int q_pitch; int64_t q_batch_stride;
+  const void* k; int k_pitch; int64_t k_batch_stride;
+  const void* v; int v_pitch; int64_t v_batch_stride;
+  void* out; int out_pitch; int64_t out_batch_stride;
+  float scale;               /* softmax(scale * q k^T) */
+} ladi_attn_desc;
+LADI_API int ladi_attention_bf16(const ladi_attn_desc* d, void* stream);
+
+/* ---- normalisation ---------------------------------------------------------------------------------------------------
+ * GroupNorm(+SiLU) over the channel-concat of up to two NHWC sources (diffusers ResnetBlock2D.norm1/norm2,
+ * Transformer2DModel.norm, conv_norm_out; VAE conv_norm_out vae.py:115-116,200-201), two passes:
+ *   stats: partial sums per (image, pixel chunk, group) -> ws[n][chunks][groups][2] fp32 (chunks returned by the query);
+ *   apply: y = (x-mean)*rstd*gamma+beta, optional SiLU, optional "+ add" AFTER the activation (vae.py:204-205), bf16 out
+ *          of pitch out_pitch holding the concatenated, normalised tensor. */
+LADI_API int ladi_groupnorm_chunks(int hw);
+LADI_API int ladi_groupnorm_stats(const void* x0, int c0, int pitch0, const void* x1, int c1, int pitch1, int n, int hw, int groups,
+                         float* ws, void* stream);
+LADI_API int ladi_groupnorm_apply(const void* x0, int c0, int pitch0, const void* x1, int c1, int pitch1, int n, int hw, int groups,
+                         const float* ws, const float* gamma, const float* beta, float eps, int silu, const void* add,
+                         int add_pitch, void* out, int out_pitch, void* stream);
+/* LayerNorm over the last dim (BasicTransformerBlock.norm1/2/3; inversion adapter LayerNorms). */
+LADI_API int ladi_layernorm(const void* x, int x_pitch, int rows, int c, const float* gamma, const float* beta, float eps, void* out,
+                   int out_pitch, void* stream);
+/* Row softmax fp32 -> bf16 (VAE mid-block AttentionBlock: softmax in fp32, Appendix A.5). */
+LADI_API int ladi_softmax_rows(const float* s, int rows, int cols, int s_pitch, float scale, void* out, int out_pitch, void* stream);
+
+/* ---- pointwise glue ------------------------------------------------------------------------------------------------- */
+/* out = a + b (bf16, equal pitch-free dense [count]); VAE decoder `sample += int_feat` (vae.py:193). */
+LADI_API int ladi_add_bf16(const void* a, const void* b, void* out, int64_t count, void* stream);
+/* nearest 2x upsample NHWC (diffusers Upsample2D F.interpolate(scale_factor=2, mode="nearest")). */
+LADI_API int ladi_upsample2x_nhwc(const void* x, int n, int h, int w, int c, void* out, void* stream);
+/* NCHW fp32 -> NHWC bf16 with channel offset/pitch (writes channels [c_off, c_off+c)); scale applied first. */
+LADI_API int ladi_nchw_f32_to_nhwc_bf16(const float* x, int n, int c, int h, int w, float scale, void* out, int out_pitch, int c_off,
+                               void* stream);
+/* NHWC (bf16 or fp32) -> NCHW fp32, channels [c_off, c_off+c) of an NHWC tensor of given pitch. */
+LADI_API int ladi_nhwc_to_nchw_f32(const void* x, int x_is_fp32, int n, int c, int h, int w, int x_pitch, int c_off, float* out,
+                          void* stream);
+/* DiagonalGaussianDistribution.sample * scaling_factor (vae.py:330-348; tryon_pipe.py:647,462):
+ * moments NHWC fp32 [n,h,w,2*cz] -> latents NCHW fp32 [n,cz,h,w] = (mean + exp(0.5*clamp(logvar,-30,20))*noise) * scale. */
+LADI_API int ladi_posterior_sample(const float* moments, int m_pitch, const float* noise_nchw, int n, int cz, int h, int w, float scale,
+                          float* out_nchw, void* stream);
+/* mask (1 - m) rows for EMASC mask_features (src/utils/data_utils.py:9-14): mask NCHW fp32 [n,1,H,W] nearest-resized by
+ * integer factor f to [n, H/f, W/f] and written as 1-m (fp32 per output pixel). */
+LADI_API int ladi_inv_mask_rows(const float* mask, int n, int H, int W, int f, float* out, void* stream);
+/* bilinear /8 downsample, align_corners=False, no antialias (tryon_pipe.py:632-634), NCHW fp32 -> NCHW fp32. */
+LADI_API int ladi_bilinear_down8(const float* x, int n, int c, int H, int W, float* out, void* stream);
+/* One DDIM step with classifier-free guidance and re-assembly of the next UNet input (tryon_pipe.py:715,735-741 +
+ * DDIMScheduler.step): eps NHWC fp32 [cfg?2B:B, h, w, eps_pitch] (first 4 channels), latents NCHW fp32 [B,4,h,w] updated
+ * in place; unet_in NHWC bf16 [cfg?2B:B, h, w, in_pitch] channels 0..3 rewritten for both halves.  coef = device table
+ * [steps][4] = {1/sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev)}, indexed by *step_ptr, which is then incremented
+ * by the last block when advance != 0. */
+LADI_API int ladi_ddim_cfg_step(const float* eps, int eps_pitch, float* latents, void* unet_in, int in_pitch, int B, int h, int w,
+                       int cfg, float guidance, const float* coef, int* step_ptr, int advance, void* stream);
+/* (x/2+0.5).clamp(0,1) NHWC bf16/fp32 [n,h,w,pitch] (first 3 channels) -> NHWC fp32 [n,h,w,3] (tryon_pipe.py:356-358). */
+LADI_API int ladi_image_out(const void* x, int x_is_fp32, int n, int h, int w, int x_pitch, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

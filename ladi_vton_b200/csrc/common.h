@@ -1,0 +1,39 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting and TMA tensor-map encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ladi_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+// thread-local last error (ladi_last_error); every entry point returns 0 on success, non-zero otherwise,
+// and never throws or aborts across the ABI.
+void ladi_set_error(const char* fmt, ...);
+
+#define LADI_CHECK(cond, ...)       \
+  do {                              \
+    if (!(cond)) {                  \
+      ladi_set_error(__VA_ARGS__);  \
+      return LADI_ERR_INVALID;      \
+    }                               \
+  } while (0)
+
+#define LADI_CUDA(call)                                                                          \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess) {                                                                    \
+      ladi_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return LADI_ERR_CUDA;                                                                      \
+    }                                                                                            \
+  } while (0)
+
+// Encodes a bf16 tensor map (rank <= 5), SWIZZLE_128B, zero OOB fill.  dims/box innermost first; strides in BYTES for
+// dims 1..rank-1.  Returns 0 on success.
+int ladi_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                          const uint32_t* box);
+
+int ladi_num_sms();

@@ -1,0 +1,453 @@
+// HBM-bound kernels of the try-on path: GroupNorm (two-source, NHWC), LayerNorm, row softmax, layout conversion, posterior
+// sampling, mask/pose resizing, the fused CFG + DDIM step, image clamp.  All loads/stores are 16-byte vectors on the
+// contiguous channel dimension (NHWC) so every warp request is fully coalesced.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = ptx::bf16_lo(u.x); f[1] = ptx::bf16_hi(u.x); f[2] = ptx::bf16_lo(u.y); f[3] = ptx::bf16_hi(u.y);
+  f[4] = ptx::bf16_lo(u.z); f[5] = ptx::bf16_hi(u.z); f[6] = ptx::bf16_lo(u.w); f[7] = ptx::bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(ptx::pack_bf16(f[0], f[1]), ptx::pack_bf16(f[2], f[3]), ptx::pack_bf16(f[4], f[5]), ptx::pack_bf16(f[6], f[7]));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+constexpr int GN_MAX_GROUPS = 64;
+constexpr int GN_MAX_CHUNKS = 64;
+
+__host__ __device__ inline int gn_chunks(int hw) {
+  int c = (hw + 63) / 64;
+  return c > GN_MAX_CHUNKS ? GN_MAX_CHUNKS : (c < 1 ? 1 : c);
+}
+
+// ---- GroupNorm pass 1: per (image, pixel chunk) partial {sum, sum of squares} per group
+__global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x0, int c0, int pitch0, const bf16* __restrict__ x1,
+                                                       int c1, int pitch1, int hw, int groups, int chunks, float* __restrict__ ws) {
+  __shared__ float sg[GN_MAX_GROUPS * 2];
+  const int n = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
+  const int C = c0 + c1, nv = C >> 3, cpg = C / groups;
+  for (int i = t; i < groups * 2; i += 256) sg[i] = 0.f;
+  __syncthreads();
+  const int per = (hw + chunks - 1) / chunks;
+  const int p0 = chunk * per, p1 = min(hw, p0 + per);
+  const int lanes_v = nv < 256 ? nv : 256;
+  const int k = 256 / lanes_v;
+  if (t < lanes_v * k) {
+    const int tv = t % lanes_v, tp = t / lanes_v;
+    for (int v = tv; v < nv; v += lanes_v) {
+      const int ch = v * 8;
+      const bf16* base;
+      int pitch;
+      if (ch < c0) { base = x0 + (size_t)n * hw * pitch0 + ch; pitch = pitch0; }
+      else { base = x1 + (size_t)n * hw * pitch1 + (ch - c0); pitch = pitch1; }
+      float s[8], q[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+      for (int px = p0 + tp; px < p1; px += k) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (size_t)px * pitch));
+        float f[8];
+        unpack8(u, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+      }
+      // fold the 8 channels into their groups (runs of equal group id), one shared atomic per run
+      int g = ch / cpg;
+      float as = 0.f, aq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int gi = (ch + i) / cpg;
+        if (gi != g) { atomicAdd(&sg[2 * g], as); atomicAdd(&sg[2 * g + 1], aq); g = gi; as = aq = 0.f; }
+        as += s[i]; aq += q[i];
+      }
+      atomicAdd(&sg[2 * g], as); atomicAdd(&sg[2 * g + 1], aq);
+    }
+  }
+  __syncthreads();
+  float* dst = ws + ((size_t)n * chunks + chunk) * groups * 2;
+  for (int i = t; i < groups * 2; i += 256) dst[i] = sg[i];
+}
+
+// ---- GroupNorm pass 2: normalise + affine (+SiLU) (+add), writes the concatenated tensor
+__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x0, int c0, int pitch0, const bf16* __restrict__ x1,
+                                                       int c1, int pitch1, int hw, int groups, int chunks, const float* __restrict__ ws,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                       int silu, const bf16* __restrict__ add, int add_pitch, bf16* __restrict__ out,
+                                                       int out_pitch, int px_per_block) {
+  __shared__ float smean[GN_MAX_GROUPS], srstd[GN_MAX_GROUPS];
+  const int n = blockIdx.y, t = threadIdx.x;
+  const int C = c0 + c1, nv = C >> 3, cpg = C / groups;
+  if (t < groups) {
+    float s = 0.f, q = 0.f;
+    const float* src = ws + (size_t)n * chunks * groups * 2 + t * 2;
+    for (int c = 0; c < chunks; ++c) { s += src[(size_t)c * groups * 2]; q += src[(size_t)c * groups * 2 + 1]; }
+    const float cnt = (float)hw * (float)cpg;
+    const float mean = s / cnt;
+    const float var = fmaxf(q / cnt - mean * mean, 0.f);
+    smean[t] = mean;
+    srstd[t] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const int p0 = blockIdx.x * px_per_block, p1 = min(hw, p0 + px_per_block);
+  const int total = (p1 - p0) * nv;
+  for (int e = t; e < total; e += 256) {
+    const int px = p0 + e / nv, v = e % nv, ch = v * 8;
+    const bf16* src = ch < c0 ? x0 + ((size_t)n * hw + px) * pitch0 + ch : x1 + ((size_t)n * hw + px) * pitch1 + (ch - c0);
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
+    float f[8];
+    unpack8(u, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (ch + i) / cpg;
+      float y = (f[i] - smean[g]) * srstd[g] * __ldg(gamma + ch + i) + __ldg(beta + ch + i);
+      if (silu) y = y / (1.f + __expf(-y));
+      f[i] = y;
+    }
+    if (add != nullptr) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(add + ((size_t)n * hw + px) * add_pitch + ch));
+      float g8[8];
+      unpack8(a, g8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += g8[i];
+    }
+    *reinterpret_cast<uint4*>(out + ((size_t)n * hw + px) * out_pitch + ch) = pack8(f);
+  }
+}
+
+// ---- LayerNorm: one warp per row, row cached in registers (C <= 2048)
+__global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, int x_pitch, int rows, int C,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                        bf16* __restrict__ out, int out_pitch) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nv = C >> 3;
+  float f[8][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int v = lane + 32 * j;
+    if (v < nv) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (size_t)row * x_pitch + v * 8));
+      unpack8(u, f[j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += f[j][i];
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (lane + 32 * j < nv) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = f[j][i] - mean; q += d * d; }
+    }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int v = lane + 32 * j;
+    if (v < nv) {
+      float y[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = (f[j][i] - mean) * rstd * __ldg(gamma + v * 8 + i) + __ldg(beta + v * 8 + i);
+      *reinterpret_cast<uint4*>(out + (size_t)row * out_pitch + v * 8) = pack8(y);
+    }
+  }
+}
+
+// ---- row softmax fp32 -> bf16
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, int cols, int s_pitch, float scale,
+                                                           bf16* __restrict__ out, int out_pitch) {
+  __shared__ float red[8];
+  const float* row = s + (size_t)blockIdx.x * s_pitch;
+  bf16* orow = out + (size_t)blockIdx.x * out_pitch;
+  const int t = threadIdx.x;
+  float mx = -INFINITY;
+  for (int c = t; c < cols; c += 256) mx = fmaxf(mx, row[c]);
+  mx = warp_max(mx);
+  if ((t & 31) == 0) red[t >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = t; c < cols; c += 256) sum += __expf((row[c] - mx) * scale);
+  sum = warp_sum(sum);
+  if ((t & 31) == 0) red[t >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  for (int c = t; c < cols; c += 256) orow[c] = __float2bfloat16(__expf((row[c] - mx) * scale) * inv);
+}
+
+__global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o, int64_t nvec) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float x[8], y[8];
+    unpack8(__ldg(a + i), x);
+    unpack8(__ldg(b + i), y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += y[j];
+    o[i] = pack8(x);
+  }
+}
+
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, int n, int h, int w, int cv, uint4* __restrict__ out) {
+  const int64_t total = (int64_t)n * (2 * h) * (2 * w) * cv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    int64_t r = i / cv;
+    const int ox = (int)(r % (2 * w)); r /= (2 * w);
+    const int oy = (int)(r % (2 * h));
+    const int b = (int)(r / (2 * h));
+    out[i] = __ldg(x + (((int64_t)b * h + (oy >> 1)) * w + (ox >> 1)) * cv + v);
+  }
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int n, int c, int hw, float scale, bf16* __restrict__ out,
+                                    int out_pitch, int c_off) {
+  const int64_t total = (int64_t)n * hw * c;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c);
+    const int64_t r = i / c;  // r = b*hw + px
+    const int64_t b = r / hw, px = r % hw;
+    out[r * out_pitch + c_off + ch] = __float2bfloat16(x[(b * c + ch) * hw + px] * scale);
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int is_f32, int n, int c, int hw, int x_pitch, int c_off,
+                                    float* __restrict__ out) {
+  const int64_t total = (int64_t)n * c * hw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t px = i % hw;
+    const int64_t r = i / hw;
+    const int ch = (int)(r % c);
+    const int64_t b = r / c;
+    const int64_t src = (b * hw + px) * x_pitch + c_off + ch;
+    out[i] = is_f32 ? reinterpret_cast<const float*>(x)[src] : __bfloat162float(reinterpret_cast<const bf16*>(x)[src]);
+  }
+}
+
+__global__ void posterior_kernel(const float* __restrict__ mom, int m_pitch, const float* __restrict__ noise, int n, int cz, int hw,
+                                 float scale, float* __restrict__ out) {
+  const int64_t total = (int64_t)n * cz * hw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t px = i % hw;
+    const int64_t r = i / hw;
+    const int ch = (int)(r % cz);
+    const int64_t b = r / cz;
+    const float* m = mom + (b * hw + px) * m_pitch;
+    const float mean = m[ch];
+    const float logvar = fminf(fmaxf(m[cz + ch], -30.f), 20.f);
+    out[i] = (mean + expf(0.5f * logvar) * noise[i]) * scale;
+  }
+}
+
+__global__ void inv_mask_kernel(const float* __restrict__ mask, int n, int H, int W, int f, float* __restrict__ out) {
+  const int h = H / f, w = W / f;
+  const int64_t total = (int64_t)n * h * w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    const int64_t r = i / w;
+    const int y = (int)(r % h);
+    const int64_t b = r / h;
+    out[i] = 1.f - mask[(b * H + (int64_t)y * f) * W + (int64_t)x * f];  // nearest: src index = floor(dst * f)
+  }
+}
+
+// F.interpolate(mode="bilinear", align_corners=False), exact /8: src = (dst+0.5)*8-0.5 = 8*dst+3.5 -> taps 8d+3, 8d+4 at 0.5
+__global__ void bilinear8_kernel(const float* __restrict__ x, int nc, int H, int W, float* __restrict__ out) {
+  const int h = H / 8, w = W / 8;
+  const int64_t total = (int64_t)nc * h * w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % w);
+    const int64_t r = i / w;
+    const int oy = (int)(r % h);
+    const int64_t p = r / h;
+    const float* s = x + (p * H + (int64_t)oy * 8 + 3) * W + (int64_t)ox * 8 + 3;
+    // same association order as ATen's upsample_bilinear2d: lerp in x on both rows, then lerp in y (weights 0.5/0.5)
+    const float top = 0.5f * s[0] + 0.5f * s[1];
+    const float bot = 0.5f * s[W] + 0.5f * s[W + 1];
+    out[i] = 0.5f * top + 0.5f * bot;
+  }
+}
+
+__global__ void ddim_cfg_kernel(const float* __restrict__ eps, int eps_pitch, float* __restrict__ lat, bf16* __restrict__ uin,
+                                int in_pitch, int B, int hw, int cfg, float guidance, const float* __restrict__ coef, int* step_ptr,
+                                int advance) {
+  const int s = step_ptr ? step_ptr[0] : 0;
+  const float inv_sa = coef[4 * s], s1a = coef[4 * s + 1], sap = coef[4 * s + 2], s1ap = coef[4 * s + 3];
+  const int64_t total = (int64_t)B * 4 * hw;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t px = i % hw;
+    const int64_t r = i / hw;
+    const int ch = (int)(r % 4);
+    const int64_t b = r / 4;
+    float e = eps[(b * hw + px) * eps_pitch + ch];
+    if (cfg) {
+      const float et = eps[((B + b) * hw + px) * eps_pitch + ch];
+      e = e + guidance * (et - e);
+    }
+    const float x = lat[i];
+    const float x0 = (x - s1a * e) * inv_sa;
+    const float xn = sap * x0 + s1ap * e;
+    lat[i] = xn;
+    const bf16 hb = __float2bfloat16(xn);
+    uin[(b * hw + px) * in_pitch + ch] = hb;
+    if (cfg) uin[((B + b) * hw + px) * in_pitch + ch] = hb;
+  }
+  if (advance && step_ptr) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int ticket = atomicAdd(step_ptr + 1, 1);
+      if (ticket == (int)gridDim.x - 1) {
+        step_ptr[1] = 0;
+        step_ptr[0] = s + 1;
+      }
+    }
+  }
+}
+
+__global__ void image_out_kernel(const void* __restrict__ x, int is_f32, int64_t npx, int x_pitch, float* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npx * 3; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t px = i / 3;
+    const int ch = (int)(i % 3);
+    const float v = is_f32 ? reinterpret_cast<const float*>(x)[px * x_pitch + ch]
+                           : __bfloat162float(reinterpret_cast<const bf16*>(x)[px * x_pitch + ch]);
+    out[i] = fminf(fmaxf(v * 0.5f + 0.5f, 0.f), 1.f);
+  }
+}
+
+inline int grid_for(int64_t total, int block = 256) {
+  int64_t g = (total + block - 1) / block;
+  const int64_t cap = (int64_t)ladi_num_sms() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+#define STREAM reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" int ladi_groupnorm_chunks(int hw) { return gn_chunks(hw); }
+
+static int gn_check(const void* x0, int c0, int pitch0, const void* x1, int c1, int pitch1, int groups) {
+  LADI_CHECK(x0 != nullptr && c0 > 0 && c0 % 8 == 0 && pitch0 % 8 == 0, "groupnorm source 0 invalid");
+  LADI_CHECK((x1 == nullptr && c1 == 0) || (x1 != nullptr && c1 % 8 == 0 && pitch1 % 8 == 0), "groupnorm source 1 invalid");
+  LADI_CHECK(groups > 0 && groups <= GN_MAX_GROUPS && (c0 + c1) % groups == 0, "groupnorm: C %% groups != 0 or groups > 64");
+  return LADI_OK;
+}
+
+extern "C" int ladi_groupnorm_stats(const void* x0, int c0, int pitch0, const void* x1, int c1, int pitch1, int n, int hw, int groups,
+                                    float* ws, void* stream) {
+  if (int e = gn_check(x0, c0, pitch0, x1, c1, pitch1, groups)) return e;
+  const int chunks = gn_chunks(hw);
+  gn_stats_kernel<<<dim3(chunks, n), 256, 0, STREAM>>>((const bf16*)x0, c0, pitch0, (const bf16*)x1, c1, pitch1, hw, groups, chunks, ws);
+  LADI_CUDA(cudaGetLastError());
+  return LADI_OK;
+}
+
+extern "C" int ladi_groupnorm_apply(const void* x0, int c0, int pitch0, const void* x1, int c1, int pitch1, int n, int hw, int groups,
+                                    const float* ws, const float* gamma, const float* beta, float eps, int silu, const void* add,
+                                    int add_pitch, void* out, int out_pitch, void* stream) {
+  if (int e = gn_check(x0, c0, pitch0, x1, c1, pitch1, groups)) return e;
+  LADI_CHECK(out_pitch % 8 == 0 && out_pitch >= c0 + c1, "groupnorm out pitch invalid");
+  const int chunks = gn_chunks(hw);
+  const int nv = (c0 + c1) / 8;
+  int ppb = (256 * 8) / nv;  // ~8 vectors per thread
+  if (ppb < 1) ppb = 1;
+  const int blocks = (hw + ppb - 1) / ppb;
+  gn_apply_kernel<<<dim3(blocks, n), 256, 0, STREAM>>>((const bf16*)x0, c0, pitch0, (const bf16*)x1, c1, pitch1, hw, groups, chunks, ws,
+                                                       gamma, beta, eps, silu, (const bf16*)add, add_pitch, (bf16*)out, out_pitch, ppb);
+  LADI_CUDA(cudaGetLastError());
+  return LADI_OK;
+}
+
+extern "C" int ladi_layernorm(const void* x, int x_pitch, int rows, int c, const float* gamma, const float* beta, float eps, void* out,
+                              int out_pitch, void* stream) {
+  LADI_CHECK(c % 8 == 0 && c <= 2048 && x_pitch % 8 == 0 && out_pitch % 8 == 0, "layernorm: C must be a multiple of 8 and <= 2048");
+  layernorm_kernel<<<(rows + 7) / 8, 256, 0, STREAM>>>((const bf16*)x, x_pitch, rows, c, gamma, beta, eps, (bf16*)out, out_pitch);
+  LADI_CUDA(cudaGetLastError());
+  return LADI_OK;
+}
+
+extern "C" int ladi_softmax_rows(const float* s, int rows, int cols, int s_pitch, float scale, void* out, int out_pitch, void* stream) {
+  LADI_CHECK(rows > 0 && cols > 0, "softmax: empty");
+  softmax_rows_kernel<<<rows, 256, 0, STREAM>>>(s, cols, s_pitch, scale, (bf16*)out, out_pitch);
+  LADI_CUDA(cudaGetLastError());
+  return LADI_OK;
+}
+
+extern "C" int ladi_add_bf16(const void* a, const void* b, void* out, int64_t count, void* stream) {
+  LADI_CHECK(count % 8 == 0, "add: count must be a multiple of 8");
+  add_kernel<<<grid_for(count / 8), 256, 0, STREAM>>>((const uint4*)a, (const uint4*)b, (uint4*)out, count / 8);
+  LADI_CUDA(cudaGetLastError());
+  return LADI_OK;
+}
+
+extern "C" int ladi_upsample2x_nhwc(const void* x, int n, int h, int w, int c, void* out, void* stream) {
+  LADI_CHECK(c % 8 == 0, "upsample: C must be a multiple of 8");
+  upsample2x_kernel<<<grid_for((int64_t)n * 4 * h * w * (c / 8)), 256, 0, STREAM>>>((const uint4*)x, n, h, w, c / 8, (uint4*)out);
+  LADI_CUDA(cudaGetLastError());
+  return LADI_OK;
+}
+
+extern "C" int ladi_nchw_f32_to_nhwc_bf16(const float* x, int n, int c, int h, int w, float scale, void* out, int out_pitch, int c_off,
+                                          void* stream) {
+  nchw_to_nhwc_kernel<<<grid_for((int64_t)n * c * h * w), 256, 0, STREAM>>>(x, n, c, h * w, scale, (bf16*)out, out_pitch, c_off);
+  LADI_CUDA(cudaGetLastError());
+  return LADI_OK;
+}
+
+extern "C" int ladi_nhwc_to_nchw_f32(const void* x, int x_is_fp32, int n, int c, int h, int w, int x_pitch, int c_off, float* out,
+                                     void* stream) {
+  nhwc_to_nchw_kernel<<<grid_for((int64_t)n * c * h * w), 256, 0, STREAM>>>(x, x_is_fp32, n, c, h * w, x_pitch, c_off, out);
+  LADI_CUDA(cudaGetLastError());
+  return LADI_OK;
+}
+
+extern "C" int ladi_posterior_sample(const float* moments, int m_pitch, const float* noise_nchw, int n, int cz, int h, int w, float scale,
+                                     float* out_nchw, void* stream) {
+  posterior_kernel<<<grid_for((int64_t)n * cz * h * w), 256, 0, STREAM>>>(moments, m_pitch, noise_nchw, n, cz, h * w, scale, out_nchw);
+  LADI_CUDA(cudaGetLastError());
+  return LADI_OK;
+}
+
+extern "C" int ladi_inv_mask_rows(const float* mask, int n, int H, int W, int f, float* out, void* stream) {
+  LADI_CHECK(f >= 1 && H % f == 0 && W % f == 0, "inv_mask: factor must divide H and W");
+  inv_mask_kernel<<<grid_for((int64_t)n * (H / f) * (W / f)), 256, 0, STREAM>>>(mask, n, H, W, f, out);
+  LADI_CUDA(cudaGetLastError());
+  return LADI_OK;
+}
+
+extern "C" int ladi_bilinear_down8(const float* x, int n, int c, int H, int W, float* out, void* stream) {
+  LADI_CHECK(H % 8 == 0 && W % 8 == 0, "bilinear_down8: H, W must be multiples of 8");
+  bilinear8_kernel<<<grid_for((int64_t)n * c * (H / 8) * (W / 8)), 256, 0, STREAM>>>(x, n * c, H, W, out);
+  LADI_CUDA(cudaGetLastError());
+  return LADI_OK;
+}
+
+extern "C" int ladi_ddim_cfg_step(const float* eps, int eps_pitch, float* latents, void* unet_in, int in_pitch, int B, int h, int w,
+                                  int cfg, float guidance, const float* coef, int* step_ptr, int advance, void* stream) {
+  LADI_CHECK(eps && latents && unet_in && coef, "ddim: null operand");
+  ddim_cfg_kernel<<<grid_for((int64_t)B * 4 * h * w), 256, 0, STREAM>>>(eps, eps_pitch, latents, (bf16*)unet_in, in_pitch, B, h * w, cfg,
+                                                                         guidance, coef, step_ptr, advance);
+  LADI_CUDA(cudaGetLastError());
+  return LADI_OK;
+}
+
+extern "C" int ladi_image_out(const void* x, int x_is_fp32, int n, int h, int w, int x_pitch, float* out, void* stream) {
+  image_out_kernel<<<grid_for((int64_t)n * h * w * 3), 256, 0, STREAM>>>(x, x_is_fp32, (int64_t)n * h * w, x_pitch, out);
+  LADI_CUDA(cudaGetLastError());
+  return LADI_OK;
+}

@@ -1,0 +1,91 @@
+"""ctypes binding of libladi_b200.so (the C ABI declared in include/ladi_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+Build it with `python __graft_entry__.py build` (or `make -C ladi_vton_b200/csrc`).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libladi_b200.so")
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("n", C.c_int), ("h_out", C.c_int), ("w_out", C.c_int), ("c_out", C.c_int),
+        ("h_in", C.c_int), ("w_in", C.c_int),
+        ("ksize", C.c_int), ("stride", C.c_int), ("pad_lo", C.c_int),
+        ("n_src", C.c_int), ("src", C.c_void_p * 2), ("src_c", C.c_int * 2), ("src_pitch", C.c_int * 2),
+        ("n_sc", C.c_int), ("sc", C.c_void_p * 2), ("sc_c", C.c_int * 2), ("sc_pitch", C.c_int * 2),
+        ("weight", C.c_void_p), ("k_total", C.c_int), ("weight_pitch", C.c_int),
+        ("bias", C.c_void_p), ("bias_per_row", C.c_int), ("bias_step_stride", C.c_int), ("step_ptr", C.c_void_p),
+        ("residual", C.c_void_p), ("residual_pitch", C.c_int),
+        ("row_scale", C.c_void_p), ("act", C.c_int),
+        ("out", C.c_void_p), ("out_pitch", C.c_int), ("out_fp32", C.c_int), ("force_bn", C.c_int),
+    ]
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int), ("heads", C.c_int), ("nq", C.c_int), ("nkv", C.c_int),
+        ("q", C.c_void_p), ("q_pitch", C.c_int), ("q_batch_stride", C.c_int64),
+        ("k", C.c_void_p), ("k_pitch", C.c_int), ("k_batch_stride", C.c_int64),
+        ("v", C.c_void_p), ("v_pitch", C.c_int), ("v_batch_stride", C.c_int64),
+        ("out", C.c_void_p), ("out_pitch", C.c_int), ("out_batch_stride", C.c_int64),
+        ("scale", C.c_float),
+    ]
+
+
+_P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64
+SIGNATURES = {
+    "ladi_abi_version": ([], C.c_int),
+    "ladi_last_error": ([], C.c_char_p),
+    "ladi_conv2d_bf16": ([C.POINTER(ConvDesc), _P], _I),
+    "ladi_attention_bf16": ([C.POINTER(AttnDesc), _P], _I),
+    "ladi_groupnorm_chunks": ([_I], _I),
+    "ladi_groupnorm_stats": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P], _I),
+    "ladi_groupnorm_apply": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _F, _I, _P, _I, _P, _I, _P], _I),
+    "ladi_layernorm": ([_P, _I, _I, _I, _P, _P, _F, _P, _I, _P], _I),
+    "ladi_softmax_rows": ([_P, _I, _I, _I, _F, _P, _I, _P], _I),
+    "ladi_add_bf16": ([_P, _P, _P, _L, _P], _I),
+    "ladi_upsample2x_nhwc": ([_P, _I, _I, _I, _I, _P, _P], _I),
+    "ladi_nchw_f32_to_nhwc_bf16": ([_P, _I, _I, _I, _I, _F, _P, _I, _I, _P], _I),
+    "ladi_nhwc_to_nchw_f32": ([_P, _I, _I, _I, _I, _I, _I, _I, _P, _P], _I),
+    "ladi_posterior_sample": ([_P, _I, _P, _I, _I, _I, _I, _F, _P, _P], _I),
+    "ladi_inv_mask_rows": ([_P, _I, _I, _I, _I, _P, _P], _I),
+    "ladi_bilinear_down8": ([_P, _I, _I, _I, _I, _P, _P], _I),
+    "ladi_ddim_cfg_step": ([_P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _I, _P], _I),
+    "ladi_image_out": ([_P, _I, _I, _I, _I, _I, _P, _P], _I),
+}
+
+_lib = None
+launches = 0  # number of kernel-launching ABI calls made by this process (bench.py reports it as gpu_launches)
+
+
+def load():
+    """Load the extension (once).  Raises RuntimeError if it has not been built -- no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: the CUDA extension is not built (run `python __graft_entry__.py build`). "
+                           "ladi_vton_b200 has no CPU or library fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (argtypes, restype) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.argtypes, fn.restype = argtypes, restype
+    if lib.ladi_abi_version() != 1:
+        raise RuntimeError("libladi_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Invoke an ABI entry point; non-zero return -> RuntimeError(ladi_last_error())."""
+    global launches
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib.ladi_last_error().decode()}")
+    launches += 1
+    return rc

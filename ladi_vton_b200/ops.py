@@ -1,0 +1,241 @@
+"""Tensor-facing wrappers over the C ABI (include/ladi_b200.h).  PyTorch is used only for device memory, streams and
+dtype bookkeeping; every function below launches hand-written sm_100a kernels and nothing else.
+
+Activation convention: NHWC bf16 tensors [N, H, W, C] whose last dim is contiguous; a channel-sliced view is fine
+(pitch = stride of the W dim).  "Token" tensors [B, T, C] are the same memory viewed as [B, 1, T, C].
+"""
+import ctypes as C
+
+import torch
+
+from . import lib
+from .lib import AttnDesc, ConvDesc
+
+ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+BK = 64
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _nhwc(t):
+    """-> (n, h, w, c, pitch) of an NHWC view; checks the layout the kernels assume."""
+    assert t.dim() == 4 and t.stride(3) == 1, "expect NHWC with contiguous channels"
+    n, h, w, c = t.shape
+    pitch = t.stride(2)
+    assert (w == 1 or True) and t.stride(1) == pitch * w and (n == 1 or t.stride(0) == pitch * w * h), \
+        f"non-dense NHWC view: shape {tuple(t.shape)} strides {t.stride()}"
+    assert pitch % 8 == 0 and t.data_ptr() % 16 == 0, "pitch must be a multiple of 8 elements and the base 16-byte aligned"
+    return n, h, w, c, pitch
+
+
+def padded_k(channels):
+    return (channels + BK - 1) // BK * BK
+
+
+def conv2d(srcs, weight, c_out, *, ksize=3, stride=1, pad_lo=1, shortcut=(), bias=None, bias_per_row=False,
+           bias_step_stride=0, step_ptr=None, residual=None, row_scale=None, act=ACT_NONE, out=None, out_fp32=False,
+           force_bn=0):
+    """Implicit-GEMM convolution over the channel-concat of `srcs` (+ fused 1x1 over `shortcut` tensors).
+    `weight`: packed bf16 [c_out, k_total] (see weights.pack_conv).  Returns the NHWC output tensor."""
+    assert 1 <= len(srcs) <= 2 and len(shortcut) <= 2
+    d = ConvDesc()
+    n, h_in, w_in, _, _ = _nhwc(srcs[0])
+    if ksize == 3 and stride == 2:
+        h_out, w_out = (h_in + (2 if pad_lo == 1 else 1) - 3) // 2 + 1, (w_in + (2 if pad_lo == 1 else 1) - 3) // 2 + 1
+    else:
+        h_out, w_out = h_in, w_in
+    d.n, d.h_out, d.w_out, d.c_out = n, h_out, w_out, c_out
+    d.h_in, d.w_in = h_in, w_in
+    d.ksize, d.stride, d.pad_lo = ksize, stride, pad_lo
+    d.n_src = len(srcs)
+    for i, s in enumerate(srcs):
+        assert s.dtype == torch.bfloat16
+        sn, sh, sw, sc, sp = _nhwc(s)
+        assert (sn, sh, sw) == (n, h_in, w_in)
+        d.src[i], d.src_c[i], d.src_pitch[i] = s.data_ptr(), sc, sp
+    d.n_sc = len(shortcut)
+    for i, s in enumerate(shortcut):
+        assert s.dtype == torch.bfloat16
+        sn, sh, sw, sc, sp = _nhwc(s)
+        assert (sn, sh, sw) == (n, h_out, w_out)
+        d.sc[i], d.sc_c[i], d.sc_pitch[i] = s.data_ptr(), sc, sp
+    assert weight.dtype == torch.bfloat16 and weight.dim() == 2 and weight.stride(1) == 1 and weight.shape[0] >= c_out
+    d.weight, d.k_total, d.weight_pitch = weight.data_ptr(), weight.shape[1], weight.stride(0)
+    if bias is not None:
+        assert bias.dtype == torch.float32
+    d.bias, d.bias_per_row, d.bias_step_stride = (bias.data_ptr() if bias is not None else 0), int(bias_per_row), bias_step_stride
+    d.step_ptr = step_ptr.data_ptr() if step_ptr is not None else 0
+    c_eff = c_out // 2 if act == ACT_GEGLU else c_out
+    if out is None:
+        out = torch.empty((n, h_out, w_out, c_eff), dtype=torch.float32 if out_fp32 else torch.bfloat16, device=srcs[0].device)
+    on, oh, ow, oc, op = (out.shape[0], out.shape[1], out.shape[2], out.shape[3], out.stride(2))
+    assert (on, oh, ow) == (n, h_out, w_out) and oc >= c_eff and out.stride(3) == 1
+    assert out.dtype == (torch.float32 if out_fp32 else torch.bfloat16)
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.shape[:3] == out.shape[:3]
+        d.residual, d.residual_pitch = residual.data_ptr(), residual.stride(2)
+    if row_scale is not None:
+        assert row_scale.dtype == torch.float32 and row_scale.numel() == n * h_out * w_out
+        d.row_scale = row_scale.data_ptr()
+    d.act, d.out, d.out_pitch, d.out_fp32, d.force_bn = act, out.data_ptr(), op, int(out_fp32), force_bn
+    lib.call("ladi_conv2d_bf16", C.byref(d), _stream())
+    return out
+
+
+def gemm(a, weight, n_out, **kw):
+    """out[M, n_out] = epilogue(a[M, K] @ weight[n_out, K]^T); `a` may be a row-strided 2-D view."""
+    assert a.dim() == 2 and a.stride(1) == 1
+    a4 = a.as_strided((1, 1, a.shape[0], a.shape[1]), (a.stride(0) * a.shape[0], a.stride(0) * a.shape[0], a.stride(0), 1))
+    out = kw.pop("out", None)
+    res = kw.pop("residual", None)
+    if out is not None:
+        out = out.as_strided((1, 1, out.shape[0], out.shape[1]), (0, 0, out.stride(0), 1))
+    if res is not None:
+        res = res.as_strided((1, 1, res.shape[0], res.shape[1]), (0, 0, res.stride(0), 1))
+    o = conv2d([a4], weight, n_out, ksize=1, out=out, residual=res, **kw)
+    return o[0, 0]
+
+
+def attention(q, k, v, heads, scale, out=None):
+    """q [B, Nq, >=heads*64] , k/v [B, Nkv, >=heads*64] (row-strided views of fused projections are fine) -> [B, Nq, heads*64]."""
+    B, nq = q.shape[0], q.shape[1]
+    nkv = k.shape[1]
+    for t in (q, k, v):
+        assert t.dtype == torch.bfloat16 and t.stride(2) == 1
+    if out is None:
+        out = torch.empty((B, nq, heads * 64), dtype=torch.bfloat16, device=q.device)
+    d = AttnDesc()
+    d.batch, d.heads, d.nq, d.nkv = B, heads, nq, nkv
+    d.q, d.q_pitch, d.q_batch_stride = q.data_ptr(), q.stride(1), q.stride(0)
+    d.k, d.k_pitch, d.k_batch_stride = k.data_ptr(), k.stride(1), k.stride(0)
+    d.v, d.v_pitch, d.v_batch_stride = v.data_ptr(), v.stride(1), v.stride(0)
+    d.out, d.out_pitch, d.out_batch_stride = out.data_ptr(), out.stride(1), out.stride(0)
+    d.scale = scale
+    lib.call("ladi_attention_bf16", C.byref(d), _stream())
+    return out
+
+
+class GroupNormWS:
+    """Per-call workspace for the two-pass GroupNorm: [n][chunks][groups][2] fp32."""
+
+    def __init__(self, device):
+        self.device, self.buf = device, None
+
+    def get(self, n, hw, groups):
+        need = n * lib.load().ladi_groupnorm_chunks(hw) * groups * 2
+        if self.buf is None or self.buf.numel() < need:
+            self.buf = torch.empty(need, dtype=torch.float32, device=self.device)
+        return self.buf
+
+
+def groupnorm(srcs, gamma, beta, groups, eps, ws, silu=False, add=None, out=None):
+    """GroupNorm(+SiLU)(+add) over the channel-concat of 1-2 NHWC tensors; writes the concatenated normalised tensor."""
+    x0 = srcs[0]
+    n, h, w, c0, p0 = _nhwc(x0)
+    if len(srcs) > 1:
+        _, _, _, c1, p1 = _nhwc(srcs[1])
+        x1 = srcs[1]
+    else:
+        x1, c1, p1 = None, 0, 0
+    if out is None:
+        out = torch.empty((n, h, w, c0 + c1), dtype=torch.bfloat16, device=x0.device)
+    wsb = ws.get(n, h * w, groups)
+    s = _stream()
+    lib.call("ladi_groupnorm_stats", _ptr(x0), c0, p0, _ptr(x1), c1, p1, n, h * w, groups, _ptr(wsb), s)
+    lib.call("ladi_groupnorm_apply", _ptr(x0), c0, p0, _ptr(x1), c1, p1, n, h * w, groups, _ptr(wsb), _ptr(gamma), _ptr(beta),
+             eps, int(silu), _ptr(add), (add.stride(2) if add is not None else 0), _ptr(out), out.stride(2), s)
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    """x [rows, C] bf16 (row-strided ok) -> [rows, C] bf16."""
+    assert x.dim() == 2 and x.stride(1) == 1
+    if out is None:
+        out = torch.empty((x.shape[0], x.shape[1]), dtype=torch.bfloat16, device=x.device)
+    lib.call("ladi_layernorm", _ptr(x), x.stride(0), x.shape[0], x.shape[1], _ptr(gamma), _ptr(beta), eps, _ptr(out),
+             out.stride(0), _stream())
+    return out
+
+
+def softmax_rows(s, scale, out=None):
+    assert s.dtype == torch.float32 and s.dim() == 2 and s.stride(1) == 1
+    if out is None:
+        out = torch.empty(s.shape, dtype=torch.bfloat16, device=s.device)
+    lib.call("ladi_softmax_rows", _ptr(s), s.shape[0], s.shape[1], s.stride(0), scale, _ptr(out), out.stride(0), _stream())
+    return out
+
+
+def add(a, b, out=None):
+    assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape and a.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty_like(a)
+    lib.call("ladi_add_bf16", _ptr(a), _ptr(b), _ptr(out), a.numel(), _stream())
+    return out
+
+
+def upsample2x(x):
+    n, h, w, c, p = _nhwc(x)
+    assert p == c
+    out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
+    lib.call("ladi_upsample2x_nhwc", _ptr(x), n, h, w, c, _ptr(out), _stream())
+    return out
+
+
+def nchw_to_nhwc(x, out, c_off=0, scale=1.0):
+    """x NCHW fp32 -> channels [c_off, c_off+C) of the NHWC bf16 tensor `out`."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == torch.bfloat16
+    n, c, h, w = x.shape
+    lib.call("ladi_nchw_f32_to_nhwc_bf16", _ptr(x), n, c, h, w, scale, _ptr(out), out.stride(2), c_off, _stream())
+    return out
+
+
+def nhwc_to_nchw(x, c, c_off=0):
+    n, h, w, _ = x.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    lib.call("ladi_nhwc_to_nchw_f32", _ptr(x), int(x.dtype == torch.float32), n, c, h, w, x.stride(2), c_off, _ptr(out), _stream())
+    return out
+
+
+def posterior_sample(moments, noise, scale):
+    """moments NHWC fp32 [n,h,w,>=2cz], noise NCHW fp32 [n,cz,h,w] -> NCHW fp32 latents * scale."""
+    n, cz, h, w = noise.shape
+    assert moments.dtype == torch.float32 and noise.dtype == torch.float32 and noise.is_contiguous()
+    out = torch.empty_like(noise)
+    lib.call("ladi_posterior_sample", _ptr(moments), moments.stride(2), _ptr(noise), n, cz, h, w, scale, _ptr(out), _stream())
+    return out
+
+
+def inv_mask_rows(mask, f):
+    n, _, H, W = mask.shape
+    assert mask.dtype == torch.float32 and mask.is_contiguous()
+    out = torch.empty((n, H // f, W // f), dtype=torch.float32, device=mask.device)
+    lib.call("ladi_inv_mask_rows", _ptr(mask), n, H, W, f, _ptr(out), _stream())
+    return out
+
+
+def bilinear_down8(x):
+    n, c, H, W = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    out = torch.empty((n, c, H // 8, W // 8), dtype=torch.float32, device=x.device)
+    lib.call("ladi_bilinear_down8", _ptr(x), n, c, H, W, _ptr(out), _stream())
+    return out
+
+
+def ddim_cfg_step(eps, latents, unet_in, cfg, guidance, coef, step_ptr, advance=True):
+    B, _, h, w = latents.shape
+    assert eps.dtype == torch.float32 and latents.dtype == torch.float32 and latents.is_contiguous()
+    lib.call("ladi_ddim_cfg_step", _ptr(eps), eps.stride(2), _ptr(latents), _ptr(unet_in), unet_in.stride(2), B, h, w, int(cfg),
+             float(guidance), _ptr(coef), _ptr(step_ptr), int(advance), _stream())
+
+
+def image_out(x):
+    n, h, w, _ = x.shape
+    out = torch.empty((n, h, w, 3), dtype=torch.float32, device=x.device)
+    lib.call("ladi_image_out", _ptr(x), int(x.dtype == torch.float32), n, h, w, x.stride(2), _ptr(out), _stream())
+    return out

@@ -1,0 +1,285 @@
+"""GPU parity of each hand-written kernel (through the C ABI) against a plain PyTorch fp32 computation of the same op on
+the same bf16-rounded inputs.  Tolerances: outputs are bf16 (relative rounding 2^-9 = 0.2%) of fp32 accumulations, so the
+normalised max error |y - ref|_inf / |ref|_inf must be < 1e-2 (bf16 out) / 2e-3 (fp32 out)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+TOL_BF16, TOL_F32 = 1e-2, 2e-3
+
+
+def nerr(y, ref):
+    return ((y.float() - ref.float()).abs().max() / ref.float().abs().max().clamp_min(1e-6)).item()
+
+
+def rnd(shape, dev, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,K,N,bn", [(512, 320, 320, 0), (200, 64, 96, 0), (384, 1024, 640, 0), (128, 128, 4, 0),
+                                      (256, 256, 256, 32), (256, 256, 256, 64), (256, 256, 256, 128), (256, 256, 320, 160),
+                                      (256, 256, 384, 192), (256, 256, 512, 256), (3072, 320, 960, 0), (77 * 2, 1024, 640, 0)])
+def test_gemm_plain(cuda, M, K, N, bn):
+    from ladi_vton_b200 import ops, weights
+    a = rnd((M, K), cuda, 1).bfloat16()
+    w = rnd((N, K), cuda, 2, K ** -0.5)
+    b = rnd((N,), cuda, 3)
+    y = ops.gemm(a, weights.pack_linear(w), N, bias=b, force_bn=bn)
+    ref = a.float() @ w.bfloat16().float().t() + b
+    torch.cuda.synchronize()
+    assert y.shape == (M, N)
+    assert nerr(y, ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("mode", ["residual", "silu", "geglu", "fp32", "rowscale", "rowbias", "stepbias", "strided"])
+def test_gemm_epilogues(cuda, mode):
+    from ladi_vton_b200 import ops, weights
+    M, K, N = 300, 320, 640
+    a = rnd((M, K), cuda, 1).bfloat16()
+    w = rnd((N, K), cuda, 2, K ** -0.5)
+    b = rnd((N,), cuda, 3)
+    wb = w.bfloat16().float()
+    base = a.float() @ wb.t() + b
+    if mode == "residual":
+        r = rnd((M, N), cuda, 4).bfloat16()
+        y = ops.gemm(a, weights.pack_linear(w), N, bias=b, residual=r)
+        ref = base + r.float()
+    elif mode == "silu":
+        y = ops.gemm(a, weights.pack_linear(w), N, bias=b, act=ops.ACT_SILU)
+        ref = F.silu(base)
+    elif mode == "geglu":
+        wi, bi = weights.interleave_geglu(w, b)
+        y = ops.gemm(a, weights.pack_linear(wi), N, bias=bi.contiguous(), act=ops.ACT_GEGLU)
+        v, g = base.chunk(2, dim=-1)
+        ref = v * F.gelu(g)
+        assert y.shape == (M, N // 2)
+    elif mode == "fp32":
+        y = ops.gemm(a, weights.pack_linear(w), N, bias=b, out_fp32=True)
+        ref = base
+        assert y.dtype == torch.float32
+        torch.cuda.synchronize()
+        assert nerr(y, ref) < TOL_F32
+    elif mode == "rowscale":
+        rs = torch.rand(M, device=cuda)
+        y = ops.gemm(a, weights.pack_linear(w), N, bias=b, row_scale=rs)
+        ref = base * rs[:, None]
+    elif mode == "rowbias":
+        rb = rnd((M,), cuda, 5)
+        y = ops.gemm(a, weights.pack_linear(w), N, bias=rb, bias_per_row=True)
+        ref = a.float() @ wb.t() + rb[:, None]
+    elif mode == "stepbias":
+        tab = rnd((5, N), cuda, 6)
+        step = torch.tensor([3, 0], dtype=torch.int32, device=cuda)
+        y = ops.gemm(a, weights.pack_linear(w), N, bias=tab, bias_step_stride=N, step_ptr=step)
+        ref = a.float() @ wb.t() + tab[3]
+    else:  # strided A (a column slice of a wider buffer) and strided weight rows
+        big = rnd((M, 3 * K), cuda, 7).bfloat16()
+        a2 = big[:, K:2 * K]
+        wbig = weights.pack_linear(rnd((N, 2 * K), cuda, 8, K ** -0.5))
+        y = ops.gemm(a2, wbig[:, :K], N, bias=b)
+        ref = a2.float() @ wbig[:, :K].float().t() + b
+    torch.cuda.synchronize()
+    assert nerr(y, ref) < TOL_BF16
+
+
+# ------------------------------------------------------------------------------------------------ conv
+def conv_ref(xs, w, b, stride=1, pad=1, asym=False):
+    x = torch.cat([t.float().permute(0, 3, 1, 2) for t in xs], dim=1)
+    if asym:
+        x = F.pad(x, (0, 1, 0, 1))
+        pad = 0
+    y = F.conv2d(x, w.bfloat16().float(), b, stride=stride, padding=pad)
+    return y.permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 12, 64, 128), (2, 64, 48, 320, 320), (3, 8, 6, 128, 192), (2, 32, 24, 192, 640),
+                                            (1, 128, 96, 64, 64), (5, 8, 6, 64, 64), (2, 16, 12, 1280, 1280)])
+def test_conv3x3(cuda, n, h, w, cin, cout):
+    from ladi_vton_b200 import ops, weights
+    x = rnd((n, h, w, cin), cuda, 1).bfloat16()
+    wt = rnd((cout, cin, 3, 3), cuda, 2, (9 * cin) ** -0.5)
+    b = rnd((cout,), cuda, 3)
+    y = ops.conv2d([x], weights.pack_conv(wt, [cin]), cout, bias=b)
+    ref = conv_ref([x], wt, b)
+    torch.cuda.synchronize()
+    assert nerr(y, ref) < TOL_BF16
+
+
+def test_conv3x3_concat_shortcut(cuda):
+    """UNet up-block resnet conv2: 3x3 over h + fused 1x1 conv_shortcut over the (virtual) concat [x, skip]."""
+    from ladi_vton_b200 import ops, weights
+    n, h, w, c0, c1, cm, cout = 2, 32, 24, 128, 64, 128, 128
+    hmid = rnd((n, h, w, cm), cuda, 1).bfloat16()
+    x0 = rnd((n, h, w, c0), cuda, 2).bfloat16()
+    x1 = rnd((n, h, w, c1), cuda, 3).bfloat16()
+    wt = rnd((cout, cm, 3, 3), cuda, 4, (9 * cm) ** -0.5)
+    ws = rnd((cout, c0 + c1, 1, 1), cuda, 5, (c0 + c1) ** -0.5)
+    b = rnd((cout,), cuda, 6)
+    y = ops.conv2d([hmid], weights.pack_conv(wt, [cm], ws, [c0, c1]), cout, bias=b, shortcut=[x0, x1])
+    ref = conv_ref([hmid], wt, b) + conv_ref([x0, x1], ws, None, pad=0)
+    torch.cuda.synchronize()
+    assert nerr(y, ref) < TOL_BF16
+    # two-source 3x3 (concat never materialised)
+    wt2 = rnd((cout, c0 + c1, 3, 3), cuda, 7, (9 * (c0 + c1)) ** -0.5)
+    y2 = ops.conv2d([x0, x1], weights.pack_conv(wt2, [c0, c1]), cout, bias=b)
+    torch.cuda.synchronize()
+    assert nerr(y2, conv_ref([x0, x1], wt2, b)) < TOL_BF16
+
+
+@pytest.mark.parametrize("asym", [False, True])
+def test_conv3x3_stride2(cuda, asym):
+    from ladi_vton_b200 import ops, weights
+    n, h, w, c = 2, 32, 24, 128
+    x = rnd((n, h, w, c), cuda, 1).bfloat16()
+    wt = rnd((c, c, 3, 3), cuda, 2, (9 * c) ** -0.5)
+    b = rnd((c,), cuda, 3)
+    y = ops.conv2d([x], weights.pack_conv(wt, [c]), c, bias=b, stride=2, pad_lo=0 if asym else 1)
+    ref = conv_ref([x], wt, b, stride=2, asym=asym)
+    torch.cuda.synchronize()
+    assert y.shape == ref.shape
+    assert nerr(y, ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("cin,pitch,cout", [(31, 32, 320), (3, 8, 128), (4, 8, 512), (128, 128, 3), (320, 320, 4), (512, 512, 8)])
+def test_conv3x3_odd_channels(cuda, cin, pitch, cout):
+    """conv_in / conv_out shapes: channel counts that are not multiples of 64 ride on TMA zero fill + zero-padded weights."""
+    from ladi_vton_b200 import ops, weights
+    n, h, w = 2, 16, 24
+    buf = torch.zeros((n, h, w, pitch), dtype=torch.bfloat16, device=cuda)
+    buf[..., :cin] = rnd((n, h, w, cin), cuda, 1).bfloat16()
+    buf[..., cin:] = 7.0  # garbage beyond C must never be read as data
+    x = buf[..., :cin]
+    wt = rnd((cout, cin, 3, 3), cuda, 2, (9 * cin) ** -0.5)
+    b = rnd((cout,), cuda, 3)
+    opitch = (cout + 7) // 8 * 8
+    out = torch.zeros((n, h, w, opitch), dtype=torch.float32, device=cuda)
+    y = ops.conv2d([x], weights.pack_conv(wt, [cin]), cout, bias=b, out=out, out_fp32=True)[..., :cout]
+    ref = conv_ref([x], wt, b)
+    torch.cuda.synchronize()
+    assert nerr(y, ref) < TOL_F32 * 2
+
+
+def test_conv_invalid_args_error(cuda):
+    from ladi_vton_b200 import ops, weights
+    x = torch.zeros((1, 8, 8, 64), dtype=torch.bfloat16, device=cuda)
+    w = weights.pack_conv(torch.zeros(64, 64, 3, 3), [64]).to(cuda)
+    with pytest.raises(RuntimeError, match="weight K"):
+        ops.conv2d([x], w[:, :64].contiguous(), 64)
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,heads,nq,nkv", [(2, 5, 768, 768), (1, 2, 128, 128), (2, 3, 192, 192), (3, 2, 48, 48), (2, 5, 768, 77),
+                                            (1, 1, 3072, 3072), (2, 2, 200, 333)])
+def test_attention(cuda, B, heads, nq, nkv):
+    from ladi_vton_b200 import ops
+    C = heads * 64
+    if nq == nkv:  # fused QKV buffer, per-head slices read in place
+        qkv = rnd((B, nq, 3 * C), cuda, 1).bfloat16()
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    else:
+        q = rnd((B, nq, C), cuda, 1).bfloat16()
+        kv = rnd((B, nkv, 2 * C), cuda, 2).bfloat16()
+        k, v = kv[..., :C], kv[..., C:]
+    y = ops.attention(q, k, v, heads, 0.125)
+    sp = lambda t: t.float().reshape(B, -1, heads, 64).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(B, nq, C)
+    torch.cuda.synchronize()
+    assert nerr(y, ref) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------ norms & glue
+@pytest.mark.parametrize("n,hw,c0,c1,groups,silu", [(2, 3072, 320, 0, 32, True), (2, 768, 1280, 640, 32, True), (3, 48, 2560, 0, 32, False),
+                                                    (2, 196608, 128, 0, 32, True), (2, 192, 64, 64, 32, True)])
+def test_groupnorm(cuda, n, hw, c0, c1, groups, silu):
+    from ladi_vton_b200 import ops
+    h, w = (hw // 48, 48) if hw % 48 == 0 else (hw, 1)
+    x0 = (rnd((n, h, w, c0), cuda, 1) * 2 + 0.5).bfloat16()
+    srcs = [x0]
+    if c1:
+        srcs.append((rnd((n, h, w, c1), cuda, 2) - 1.0).bfloat16())
+    C = c0 + c1
+    gamma, beta = rnd((C,), cuda, 3) + 1, rnd((C,), cuda, 4)
+    ws = ops.GroupNormWS(cuda)
+    y = ops.groupnorm(srcs, gamma, beta, groups, 1e-5, ws, silu=silu)
+    xc = torch.cat([s.float() for s in srcs], dim=-1).permute(0, 3, 1, 2)
+    ref = F.group_norm(xc, groups, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert nerr(y, ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("rows,C", [(3072, 320), (100, 640), (77, 1280), (9, 1024)])
+def test_layernorm(cuda, rows, C):
+    from ladi_vton_b200 import ops
+    x = (rnd((rows, C), cuda, 1) * 3 + 1).bfloat16()
+    g, b = rnd((C,), cuda, 2) + 1, rnd((C,), cuda, 3)
+    y = ops.layernorm(x, g, b, 1e-5)
+    ref = F.layer_norm(x.float(), (C,), g, b, 1e-5)
+    torch.cuda.synchronize()
+    assert nerr(y, ref) < TOL_BF16
+
+
+def test_softmax_rows(cuda):
+    from ladi_vton_b200 import ops
+    s = rnd((300, 3072), cuda, 1, 20.0)
+    y = ops.softmax_rows(s, 512 ** -0.5)
+    ref = torch.softmax(s * 512 ** -0.5, dim=-1)
+    torch.cuda.synchronize()
+    assert nerr(y, ref) < TOL_BF16
+
+
+def test_pointwise_glue(cuda):
+    from ladi_vton_b200 import ops
+    a, b = rnd((2, 8, 6, 64), cuda, 1).bfloat16(), rnd((2, 8, 6, 64), cuda, 2).bfloat16()
+    assert nerr(ops.add(a, b), a.float() + b.float()) < TOL_BF16
+    up = ops.upsample2x(a)
+    assert torch.equal(up, a.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2))
+    x = rnd((2, 18, 64, 48), cuda, 3).abs()
+    assert torch.allclose(ops.bilinear_down8(x), F.interpolate(x, size=(8, 6), mode="bilinear"), atol=1e-6)
+    m = (rnd((2, 1, 64, 48), cuda, 4) > 0).float()
+    for f in (1, 2, 4, 8):
+        assert torch.equal(ops.inv_mask_rows(m, f), 1 - F.interpolate(m, size=(64 // f, 48 // f))[:, 0])
+    nchw = rnd((2, 5, 8, 6), cuda, 5)
+    buf = torch.zeros((2, 8, 6, 16), dtype=torch.bfloat16, device=cuda)
+    ops.nchw_to_nhwc(nchw, buf, c_off=3, scale=2.0)
+    assert torch.equal(buf[..., 3:8], (nchw * 2).bfloat16().permute(0, 2, 3, 1))
+    assert torch.equal(ops.nhwc_to_nchw(buf, 5, 3), buf[..., 3:8].float().permute(0, 3, 1, 2))
+    mom = rnd((2, 8, 6, 8), cuda, 6)
+    noise = rnd((2, 4, 8, 6), cuda, 7)
+    z = ops.posterior_sample(mom, noise, 0.18215)
+    mean, logvar = mom[..., :4].permute(0, 3, 1, 2), mom[..., 4:].permute(0, 3, 1, 2).clamp(-30, 20)
+    assert torch.allclose(z, (mean + torch.exp(0.5 * logvar) * noise) * 0.18215, rtol=1e-5, atol=1e-6)
+    img = rnd((2, 8, 6, 4), cuda, 8)
+    assert torch.allclose(ops.image_out(img), (img[..., :3] / 2 + 0.5).clamp(0, 1), atol=1e-6)
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("cfg", [False, True])
+def test_ddim_cfg_step(cuda, cfg):
+    from ladi_vton_b200 import ops
+    B, h, w, g = 2, 8, 6, 7.5
+    Bp = 2 * B if cfg else B
+    eps = torch.zeros((Bp, h, w, 4), dtype=torch.float32, device=cuda)
+    eps[:] = rnd((Bp, h, w, 4), cuda, 1)
+    lat = rnd((B, 4, h, w), cuda, 2)
+    lat0 = lat.clone()
+    uin = torch.zeros((Bp, h, w, 32), dtype=torch.bfloat16, device=cuda)
+    coef = torch.tensor([[1.1, 0.3, 0.9, 0.2], [1.2, 0.4, 0.8, 0.1]], device=cuda)
+    step = torch.tensor([1, 0], dtype=torch.int32, device=cuda)
+    ops.ddim_cfg_step(eps, lat, uin, cfg, g, coef, step)
+    e = eps.permute(0, 3, 1, 2)
+    if cfg:
+        e = e[:B] + g * (e[B:] - e[:B])
+    ref = 0.8 * ((lat0 - 0.4 * e) * 1.2) + 0.1 * e
+    torch.cuda.synchronize()
+    assert torch.allclose(lat, ref, rtol=1e-5, atol=1e-5)
+    assert step.tolist() == [2, 0]
+    assert torch.equal(uin[:B, ..., :4], ref.bfloat16().permute(0, 2, 3, 1))
+    if cfg:
+        assert torch.equal(uin[B:, ..., :4], uin[:B, ..., :4])

@@ -120,9 +120,11 @@ LADI_API int ladi_softmax_rows(const float* s, int rows, int cols, int s_pitch, 
 LADI_API int ladi_add_bf16(const void* a, const void* b, void* out, int64_t count, void* stream);
 /* nearest 2x upsample NHWC (diffusers Upsample2D F.interpolate(scale_factor=2, mode="nearest")). */
 LADI_API int ladi_upsample2x_nhwc(const void* x, int n, int h, int w, int c, void* out, void* stream);
-/* NCHW fp32 -> NHWC bf16 with channel offset/pitch (writes channels [c_off, c_off+c)); scale applied first. */
-LADI_API int ladi_nchw_f32_to_nhwc_bf16(const float* x, int n, int c, int h, int w, float scale, void* out, int out_pitch, int c_off,
-                               void* stream);
+/* NCHW fp32 [n,c,h*f,w*f] -> NHWC bf16 [n,h,w,pitch] channels [c_off, c_off+c): nearest sampling every f-th pixel
+ * (F.interpolate default mode, tryon_pipe.py:434-436), times `scale`, optionally gated by (gate[n,0,..] < 0.5) -- the
+ * `masked_image = image * (mask < 0.5)` of diffusers prepare_mask_and_masked_image (call-site tryon_pipe.py:630). */
+LADI_API int ladi_nchw_f32_to_nhwc_bf16(const float* x, int n, int c, int h, int w, int f, float scale, const float* gate, void* out,
+                               int out_pitch, int c_off, void* stream);
 /* NHWC (bf16 or fp32) -> NCHW fp32, channels [c_off, c_off+c) of an NHWC tensor of given pitch. */
 LADI_API int ladi_nhwc_to_nchw_f32(const void* x, int x_is_fp32, int n, int c, int h, int w, int x_pitch, int c_off, float* out,
                           void* stream);

@@ -1,0 +1,11 @@
+"""ladi_vton_b200 -- B200-native (sm_100a) engine for the LaDI-VTON try-on inference path.
+
+Public surface mirrors the reference (miccunifi/ladi-vton): `StableDiffusionTryOnePipeline` (src/vto_pipelines/tryon_pipe.py),
+`AutoencoderKL` (src/models/AutoencoderKL.py), `EMASC` (src/models/emasc.py), `UNet2DConditionModel` + `DDIMScheduler`
+(diffusers 0.14, built in hubconf.py / src/inference.py).  All arithmetic runs in libladi_b200.so (include/ladi_b200.h);
+there is no CPU or library fallback.
+"""
+from .pipeline import StableDiffusionPipelineOutput, StableDiffusionTryOnePipeline  # noqa: F401
+from .scheduler import DDIMScheduler  # noqa: F401
+from .unet import UNet2DConditionModel, unet_param_shapes  # noqa: F401
+from .vae import EMASC, AutoencoderKL, vae_param_shapes  # noqa: F401

@@ -214,14 +214,21 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, int n, int h, int
   }
 }
 
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int n, int c, int hw, float scale, bf16* __restrict__ out,
-                                    int out_pitch, int c_off) {
+// out[b, y, x, c_off + ch] = src[b, ch, y*f, x*f] * scale * (gate ? (gate[b, 0, y*f, x*f] < 0.5) : 1)
+// (f > 1: nearest down-sampling, src index = floor(dst * f); gate: `image * (mask < 0.5)` of prepare_mask_and_masked_image)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int n, int c, int h, int w, int f, float scale,
+                                    const float* __restrict__ gate, bf16* __restrict__ out, int out_pitch, int c_off) {
+  const int64_t hw = (int64_t)h * w;
   const int64_t total = (int64_t)n * hw * c;
+  const int64_t W = (int64_t)w * f, HW = (int64_t)h * f * W;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int ch = (int)(i % c);
     const int64_t r = i / c;  // r = b*hw + px
     const int64_t b = r / hw, px = r % hw;
-    out[r * out_pitch + c_off + ch] = __float2bfloat16(x[(b * c + ch) * hw + px] * scale);
+    const int64_t sp = (px / w) * f * W + (px % w) * f;
+    float v = x[(b * c + ch) * HW + sp] * scale;
+    if (gate != nullptr && !(gate[b * HW + sp] < 0.5f)) v = 0.f;
+    out[r * out_pitch + c_off + ch] = __float2bfloat16(v);
   }
 }
 
@@ -402,9 +409,10 @@ extern "C" int ladi_upsample2x_nhwc(const void* x, int n, int h, int w, int c, v
   return LADI_OK;
 }
 
-extern "C" int ladi_nchw_f32_to_nhwc_bf16(const float* x, int n, int c, int h, int w, float scale, void* out, int out_pitch, int c_off,
-                                          void* stream) {
-  nchw_to_nhwc_kernel<<<grid_for((int64_t)n * c * h * w), 256, 0, STREAM>>>(x, n, c, h * w, scale, (bf16*)out, out_pitch, c_off);
+extern "C" int ladi_nchw_f32_to_nhwc_bf16(const float* x, int n, int c, int h, int w, int f, float scale, const float* gate, void* out,
+                                          int out_pitch, int c_off, void* stream) {
+  LADI_CHECK(f >= 1, "nchw_to_nhwc: bad sampling factor");
+  nchw_to_nhwc_kernel<<<grid_for((int64_t)n * c * h * w), 256, 0, STREAM>>>(x, n, c, h, w, f, scale, gate, (bf16*)out, out_pitch, c_off);
   LADI_CUDA(cudaGetLastError());
   return LADI_OK;
 }

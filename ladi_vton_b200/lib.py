@@ -49,7 +49,7 @@ SIGNATURES = {
     "ladi_softmax_rows": ([_P, _I, _I, _I, _F, _P, _I, _P], _I),
     "ladi_add_bf16": ([_P, _P, _P, _L, _P], _I),
     "ladi_upsample2x_nhwc": ([_P, _I, _I, _I, _I, _P, _P], _I),
-    "ladi_nchw_f32_to_nhwc_bf16": ([_P, _I, _I, _I, _I, _F, _P, _I, _I, _P], _I),
+    "ladi_nchw_f32_to_nhwc_bf16": ([_P, _I, _I, _I, _I, _I, _F, _P, _P, _I, _I, _P], _I),
     "ladi_nhwc_to_nchw_f32": ([_P, _I, _I, _I, _I, _I, _I, _I, _P, _P], _I),
     "ladi_posterior_sample": ([_P, _I, _P, _I, _I, _I, _I, _F, _P, _P], _I),
     "ladi_inv_mask_rows": ([_P, _I, _I, _I, _I, _P, _P], _I),

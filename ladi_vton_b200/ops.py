@@ -187,11 +187,14 @@ def upsample2x(x):
     return out
 
 
-def nchw_to_nhwc(x, out, c_off=0, scale=1.0):
-    """x NCHW fp32 -> channels [c_off, c_off+C) of the NHWC bf16 tensor `out`."""
+def nchw_to_nhwc(x, out, c_off=0, scale=1.0, f=1, gate=None):
+    """x NCHW fp32 (sampled every f-th pixel, optionally gated by gate<0.5) -> channels [c_off, c_off+C) of NHWC bf16 `out`."""
     assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == torch.bfloat16
-    n, c, h, w = x.shape
-    lib.call("ladi_nchw_f32_to_nhwc_bf16", _ptr(x), n, c, h, w, scale, _ptr(out), out.stride(2), c_off, _stream())
+    n, c, H, W = x.shape
+    assert H % f == 0 and W % f == 0 and out.shape[1] == H // f and out.shape[2] == W // f and out.shape[0] == n
+    if gate is not None:
+        assert gate.dtype == torch.float32 and gate.is_contiguous() and gate.shape == (n, 1, H, W)
+    lib.call("ladi_nchw_f32_to_nhwc_bf16", _ptr(x), n, c, H // f, W // f, f, scale, _ptr(gate), _ptr(out), out.stride(2), c_off, _stream())
     return out
 
 

@@ -13,6 +13,17 @@ from .lib import AttnDesc, ConvDesc
 
 ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
 BK = 64
+PROFILE = None  # bench.py: set to a list to bracket every launch with CUDA events -> (name, start, end, algorithmic flops)
+
+
+def _call(name, flops, *args):
+    if PROFILE is None:
+        return lib.call(name, *args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lib.call(name, *args)
+    e1.record()
+    PROFILE.append((name, e0, e1, flops))
 
 
 def _stream():
@@ -84,7 +95,9 @@ def conv2d(srcs, weight, c_out, *, ksize=3, stride=1, pad_lo=1, shortcut=(), bia
         assert row_scale.dtype == torch.float32 and row_scale.numel() == n * h_out * w_out
         d.row_scale = row_scale.data_ptr()
     d.act, d.out, d.out_pitch, d.out_fp32, d.force_bn = act, out.data_ptr(), op, int(out_fp32), force_bn
-    lib.call("ladi_conv2d_bf16", C.byref(d), _stream())
+    # algorithmic flops: 2 * output pixels * c_out * true reduction length (padding channels excluded)
+    k_true = ksize * ksize * sum(int(t.shape[3]) for t in srcs) + sum(int(t.shape[3]) for t in shortcut)
+    _call("ladi_conv2d_bf16", 2.0 * n * h_out * w_out * c_out * k_true, C.byref(d), _stream())
     return out
 
 
@@ -117,7 +130,7 @@ def attention(q, k, v, heads, scale, out=None):
     d.v, d.v_pitch, d.v_batch_stride = v.data_ptr(), v.stride(1), v.stride(0)
     d.out, d.out_pitch, d.out_batch_stride = out.data_ptr(), out.stride(1), out.stride(0)
     d.scale = scale
-    lib.call("ladi_attention_bf16", C.byref(d), _stream())
+    _call("ladi_attention_bf16", 4.0 * B * heads * nq * nkv * 64, C.byref(d), _stream())
     return out
 
 
@@ -147,8 +160,8 @@ def groupnorm(srcs, gamma, beta, groups, eps, ws, silu=False, add=None, out=None
         out = torch.empty((n, h, w, c0 + c1), dtype=torch.bfloat16, device=x0.device)
     wsb = ws.get(n, h * w, groups)
     s = _stream()
-    lib.call("ladi_groupnorm_stats", _ptr(x0), c0, p0, _ptr(x1), c1, p1, n, h * w, groups, _ptr(wsb), s)
-    lib.call("ladi_groupnorm_apply", _ptr(x0), c0, p0, _ptr(x1), c1, p1, n, h * w, groups, _ptr(wsb), _ptr(gamma), _ptr(beta),
+    _call("ladi_groupnorm_stats", 0.0, _ptr(x0), c0, p0, _ptr(x1), c1, p1, n, h * w, groups, _ptr(wsb), s)
+    _call("ladi_groupnorm_apply", 0.0, _ptr(x0), c0, p0, _ptr(x1), c1, p1, n, h * w, groups, _ptr(wsb), _ptr(gamma), _ptr(beta),
              eps, int(silu), _ptr(add), (add.stride(2) if add is not None else 0), _ptr(out), out.stride(2), s)
     return out
 
@@ -158,7 +171,7 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
     assert x.dim() == 2 and x.stride(1) == 1
     if out is None:
         out = torch.empty((x.shape[0], x.shape[1]), dtype=torch.bfloat16, device=x.device)
-    lib.call("ladi_layernorm", _ptr(x), x.stride(0), x.shape[0], x.shape[1], _ptr(gamma), _ptr(beta), eps, _ptr(out),
+    _call("ladi_layernorm", 0.0, _ptr(x), x.stride(0), x.shape[0], x.shape[1], _ptr(gamma), _ptr(beta), eps, _ptr(out),
              out.stride(0), _stream())
     return out
 
@@ -183,7 +196,7 @@ def upsample2x(x):
     n, h, w, c, p = _nhwc(x)
     assert p == c
     out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
-    lib.call("ladi_upsample2x_nhwc", _ptr(x), n, h, w, c, _ptr(out), _stream())
+    _call("ladi_upsample2x_nhwc", 0.0, _ptr(x), n, h, w, c, _ptr(out), _stream())
     return out
 
 

@@ -15,7 +15,7 @@ from typing import Any
 import numpy as np
 import torch
 
-from . import ops
+from . import lib, ops
 
 
 @dataclass
@@ -277,16 +277,23 @@ class StableDiffusionTryOnePipeline:
             else:
                 if s.graph is None or s.guidance != guidance_scale or s.graph_key != self._graph_key() + (s.coef.data_ptr(),):
                     s.graph = torch.cuda.CUDAGraph()
+                    n0 = lib.launches
                     with torch.cuda.graph(s.graph):
                         self._step(s, cfg, guidance_scale)
+                    s.graph_nodes = lib.launches - n0
+                    lib.launches = n0  # capture records, it does not launch
                     s.guidance, s.graph_key = guidance_scale, self._graph_key() + (s.coef.data_ptr(),)
                     # capture records but does not execute: fall through to the replay below
                 s.graph.replay()
+                lib.launches += s.graph_nodes
             if callback is not None and i % callback_steps == 0:
                 callback(i, ts[i], s.latents)
         # 11. decode with the EMASC skips, clamp, D2H
         img = self.vae.decode_nhwc(s.latents, inter, self.emasc_int_layers if inter is not None else None, scale=1.0 / sf)
-        out = ops.image_out(img).cpu().numpy()  # [B, H, W, 3] fp32 in [0, 1]  (:356-358)
+        out = ops.image_out(img)  # [B, H, W, 3] fp32 in [0, 1]  (:356)
+        if output_type == "pt":  # extension: leave the result on the device (used for device-resident timing / NCCL gather)
+            return StableDiffusionPipelineOutput(images=out, nsfw_content_detected=None) if return_dict else (out, None)
+        out = out.cpu().numpy()  # (:358)
         if output_type == "pil":
             out = self.numpy_to_pil(out)
         if not return_dict:

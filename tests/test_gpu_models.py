@@ -1,0 +1,130 @@
+"""GPU parity of the assembled models and of the whole try-on pipeline against the fp32 CPU oracle (oracle/ladi_oracle),
+same seeded weights and inputs.  The engine computes in bf16 (fp32 accumulate, fp32 latents/scheduler); the stated
+tolerances are on the relative L2 error  |y - ref|_2 / |ref|_2 :
+    single UNet forward        <= 2e-2      VAE moments / decode        <= 2e-2
+    EMASC features             <= 1.5e-2    final image (few DDIM steps) mean |diff| <= 2/255 (small config), reported for full size
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(y, ref):
+    y, ref = y.detach().float().cpu(), ref.detach().float().cpu()
+    return ((y - ref).norm() / ref.norm().clamp_min(1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def small(cuda):
+    from ladi_vton_b200 import synthetic as S
+    from ladi_oracle.unet import UNet2DConditionModel as OU
+    from ladi_oracle.vae import AutoencoderKL as OV
+    from ladi_oracle.parts import EMASC as OE
+    pipe, sds = S.build_pipeline(cuda, S.SMALL_UNET, S.SMALL_VAE)
+    ou = OU(**S.SMALL_UNET).eval(); ou.load_state_dict(sds["unet"])
+    ov = OV(**S.SMALL_VAE).eval(); ov.load_state_dict(sds["vae"])
+    oe = OE(*sds["emasc_channels"]).eval(); oe.load_state_dict(sds["emasc"])
+    return pipe, ou, ov, oe
+
+
+def test_unet_small_forward(cuda, small):
+    pipe, ou, _, _ = small
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((2, 31, 16, 8), generator=g)
+    ctx = torch.randn((2, 77, 128), generator=g)
+    with torch.no_grad():
+        ref = ou(x, torch.tensor(981), ctx).sample
+    y = pipe.unet(x.to(cuda), torch.tensor(981), ctx.to(cuda)).sample
+    assert y.shape == ref.shape
+    assert rel_l2(y, ref) < 2e-2
+
+
+def test_vae_emasc_small(cuda, small):
+    pipe, _, ov, oe = small
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand((2, 3, 128, 64), generator=g) * 2 - 1
+    with torch.no_grad():
+        enc, feats = ov.encode(x)
+        ref_m = enc.latent_dist.parameters
+    mom, f = pipe.vae.encode_nhwc(x.to(cuda))
+    assert rel_l2(mom.permute(0, 3, 1, 2), ref_m) < 2e-2
+    for i in (1, 3, 4, 5):
+        assert rel_l2(f[i].permute(0, 3, 1, 2), feats[i]) < 2e-2
+    # EMASC + mask_features + decode with the skips
+    from ladi_oracle.parts import mask_features
+    mask = torch.zeros((2, 1, 128, 64)); mask[:, :, 30:100, 10:50] = 1
+    with torch.no_grad():
+        inter_ref = mask_features(oe([feats[i] for i in range(1, 6)]), mask)
+        z = torch.randn((2, 4, 16, 8), generator=g)
+        img_ref = ov.decode(z, list(inter_ref), [1, 2, 3, 4, 5]).sample
+    from ladi_vton_b200 import ops
+    md = mask.to(cuda)
+    sel = [f[i] for i in range(1, 6)]
+    inter = pipe.emasc(sel, [ops.inv_mask_rows(md, 128 // t.shape[1]) for t in sel])
+    for a, b in zip(inter, inter_ref):
+        assert rel_l2(a.permute(0, 3, 1, 2), b) < 1.5e-2
+    img = pipe.vae.decode(z.to(cuda), inter, [1, 2, 3, 4, 5]).sample
+    assert rel_l2(img, img_ref) < 2e-2
+
+
+@pytest.mark.parametrize("gs,graph", [(7.5, True), (1.0, True), (7.5, False)])
+def test_pipeline_small(cuda, small, gs, graph):
+    from ladi_vton_b200 import synthetic as S
+    from ladi_oracle.parts import DDIMScheduler
+    from ladi_oracle.pipeline import OracleTryOnPipeline
+    pipe, ou, ov, oe = small
+    inp = S.synthetic_inputs(2, 128, 64, ctx_dim=128)
+    op = OracleTryOnPipeline(ov, ou, DDIMScheduler(), oe, [1, 2, 3, 4, 5])
+    ref = op(inp["image"].clone(), inp["mask_image"].clone(), inp["pose_map"], inp["warped_cloth"], inp["prompt_embeds"],
+             inp["negative_prompt_embeds"], height=128, width=64, num_inference_steps=5, guidance_scale=gs,
+             generator=torch.Generator().manual_seed(7))
+    pipe.use_cuda_graph = graph
+    out = pipe(image=inp["image"].clone(), mask_image=inp["mask_image"].clone(), pose_map=inp["pose_map"],
+               warped_cloth=inp["warped_cloth"], prompt_embeds=inp["prompt_embeds"],
+               negative_prompt_embeds=inp["negative_prompt_embeds"], height=128, width=64, num_inference_steps=5,
+               guidance_scale=gs, generator=torch.Generator().manual_seed(7), output_type="np").images
+    assert out.shape == ref.shape == (2, 128, 64, 3)
+    assert np.abs(out - ref).mean() < 2.0 / 255
+    # second call re-uses the captured graph and must reproduce the first bit-for-bit... up to fp32 atomics in GroupNorm
+    out2 = pipe(image=inp["image"].clone(), mask_image=inp["mask_image"].clone(), pose_map=inp["pose_map"],
+                warped_cloth=inp["warped_cloth"], prompt_embeds=inp["prompt_embeds"],
+                negative_prompt_embeds=inp["negative_prompt_embeds"], height=128, width=64, num_inference_steps=5,
+                guidance_scale=gs, generator=torch.Generator().manual_seed(7), output_type="np").images
+    assert np.abs(out2 - out).mean() < 0.5 / 255
+
+
+def test_pipeline_errors(cuda, small):
+    from ladi_vton_b200 import synthetic as S
+    pipe = small[0]
+    inp = S.synthetic_inputs(1, 128, 64, ctx_dim=128)
+    kw = dict(image=inp["image"], mask_image=inp["mask_image"], pose_map=inp["pose_map"], warped_cloth=inp["warped_cloth"])
+    with pytest.raises(ValueError, match="divisible by 8"):
+        pipe(**kw, prompt_embeds=inp["prompt_embeds"], height=100, width=64)
+    with pytest.raises(ValueError, match="Provide either"):
+        pipe(**kw, height=128, width=64)
+    with pytest.raises(ValueError, match="range"):
+        pipe(**{**kw, "image": inp["image"] * 3}, prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+             height=128, width=64)
+    with pytest.raises(ValueError, match="cloth_input_type"):
+        pipe(**kw, prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"], height=128, width=64,
+             cloth_input_type="bogus")
+
+
+def test_unet_full_forward(cuda):
+    """Full SD-2-inpaint 31-channel UNet (865,988,484 parameters), one forward at 64x48 latents, CFG batch 2."""
+    from ladi_vton_b200 import UNet2DConditionModel, synthetic as S, unet_param_shapes
+    from ladi_oracle.unet import UNet2DConditionModel as OU
+    sd = S.random_state_dict(unet_param_shapes({}), 1234)
+    ou = OU().eval(); ou.load_state_dict(sd)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((2, 31, 64, 48), generator=g)
+    ctx = torch.randn((2, 77, 1024), generator=g)
+    with torch.no_grad():
+        ref = ou(x, torch.tensor(501), ctx).sample
+    unet = UNet2DConditionModel().load_state_dict(sd).to(cuda)
+    y = unet(x.to(cuda), torch.tensor(501), ctx.to(cuda)).sample
+    err = rel_l2(y, ref)
+    print("full UNet forward rel-L2 vs fp32 oracle:", err)
+    assert err < 2e-2

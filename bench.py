@@ -234,9 +234,9 @@ def main():
     s = pipe._sessions[(B, 2 * B if cfg else B, H // 8, W // 8)]
     pipe.unet.forward_nhwc(s.unet_in, s.step)
     torch.cuda.synchronize()
-    conv = [(e0.elapsed_time(e1), fl) for (name, e0, e1, fl) in ops.PROFILE if name == "ladi_conv2d_bf16"]
-    attn = [(e0.elapsed_time(e1), fl) for (name, e0, e1, fl) in ops.PROFILE if name == "ladi_attention_bf16"]
-    allk = sum(e0.elapsed_time(e1) for (_, e0, e1, _) in ops.PROFILE)
+    conv = [(e0.elapsed_time(e1), fl) for (name, e0, e1, fl, _) in ops.PROFILE if name == "ladi_conv2d_bf16"]
+    attn = [(e0.elapsed_time(e1), fl) for (name, e0, e1, fl, _) in ops.PROFILE if name == "ladi_attention_bf16"]
+    allk = sum(e0.elapsed_time(e1) for (_, e0, e1, _, _) in ops.PROFILE)
     ops.PROFILE = None
     t_conv, f_conv = sum(t for t, _ in conv), sum(f for _, f in conv)
     t_attn, f_attn = sum(t for t, _ in attn), sum(f for _, f in attn)

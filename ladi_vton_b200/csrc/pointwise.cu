@@ -32,14 +32,14 @@ __host__ __device__ inline int gn_chunks(int hw) {
   return c > GN_MAX_CHUNKS ? GN_MAX_CHUNKS : (c < 1 ? 1 : c);
 }
 
-// ---- GroupNorm pass 1: per (image, pixel chunk) partial {sum, sum of squares} per group
+// ---- GroupNorm pass 1: per (image, pixel chunk) partial {sum, sum of squares} per group.  Deterministic: per-thread channel
+// partials go to shared memory and are folded in a fixed order (no floating-point atomics), so two runs are bit-identical.
+constexpr int GN_SLOTS = 2560;  // >= max(channels, 256 threads * 8 channels)
 __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x0, int c0, int pitch0, const bf16* __restrict__ x1,
                                                        int c1, int pitch1, int hw, int groups, int chunks, float* __restrict__ ws) {
-  __shared__ float sg[GN_MAX_GROUPS * 2];
+  __shared__ float ps[GN_SLOTS], pq[GN_SLOTS];  // [pixel lane][channel]
   const int n = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
   const int C = c0 + c1, nv = C >> 3, cpg = C / groups;
-  for (int i = t; i < groups * 2; i += 256) sg[i] = 0.f;
-  __syncthreads();
   const int per = (hw + chunks - 1) / chunks;
   const int p0 = chunk * per, p1 = min(hw, p0 + per);
   const int lanes_v = nv < 256 ? nv : 256;
@@ -62,21 +62,18 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
       }
-      // fold the 8 channels into their groups (runs of equal group id), one shared atomic per run
-      int g = ch / cpg;
-      float as = 0.f, aq = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int gi = (ch + i) / cpg;
-        if (gi != g) { atomicAdd(&sg[2 * g], as); atomicAdd(&sg[2 * g + 1], aq); g = gi; as = aq = 0.f; }
-        as += s[i]; aq += q[i];
-      }
-      atomicAdd(&sg[2 * g], as); atomicAdd(&sg[2 * g + 1], aq);
+      for (int i = 0; i < 8; ++i) { ps[tp * C + ch + i] = s[i]; pq[tp * C + ch + i] = q[i]; }
     }
   }
   __syncthreads();
-  float* dst = ws + ((size_t)n * chunks + chunk) * groups * 2;
-  for (int i = t; i < groups * 2; i += 256) dst[i] = sg[i];
+  if (t < groups) {
+    float s = 0.f, q = 0.f;
+    for (int l = 0; l < k; ++l)
+      for (int c = t * cpg; c < (t + 1) * cpg; ++c) { s += ps[l * C + c]; q += pq[l * C + c]; }
+    float* dst = ws + (((size_t)n * chunks + chunk) * groups + t) * 2;
+    dst[0] = s; dst[1] = q;
+  }
 }
 
 // ---- GroupNorm pass 2: normalise + affine (+SiLU) (+add), writes the concatenated tensor
@@ -352,6 +349,7 @@ static int gn_check(const void* x0, int c0, int pitch0, const void* x1, int c1, 
   LADI_CHECK(x0 != nullptr && c0 > 0 && c0 % 8 == 0 && pitch0 % 8 == 0, "groupnorm source 0 invalid");
   LADI_CHECK((x1 == nullptr && c1 == 0) || (x1 != nullptr && c1 % 8 == 0 && pitch1 % 8 == 0), "groupnorm source 1 invalid");
   LADI_CHECK(groups > 0 && groups <= GN_MAX_GROUPS && (c0 + c1) % groups == 0, "groupnorm: C %% groups != 0 or groups > 64");
+  LADI_CHECK(c0 + c1 <= GN_SLOTS, "groupnorm: more than %d channels", GN_SLOTS);
   return LADI_OK;
 }
 

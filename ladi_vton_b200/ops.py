@@ -16,14 +16,14 @@ BK = 64
 PROFILE = None  # bench.py: set to a list to bracket every launch with CUDA events -> (name, start, end, algorithmic flops)
 
 
-def _call(name, flops, *args):
+def _call(name, flops, *args, tag=""):
     if PROFILE is None:
         return lib.call(name, *args)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     lib.call(name, *args)
     e1.record()
-    PROFILE.append((name, e0, e1, flops))
+    PROFILE.append((name, e0, e1, flops, tag))
 
 
 def _stream():
@@ -97,7 +97,8 @@ def conv2d(srcs, weight, c_out, *, ksize=3, stride=1, pad_lo=1, shortcut=(), bia
     d.act, d.out, d.out_pitch, d.out_fp32, d.force_bn = act, out.data_ptr(), op, int(out_fp32), force_bn
     # algorithmic flops: 2 * output pixels * c_out * true reduction length (padding channels excluded)
     k_true = ksize * ksize * sum(int(t.shape[3]) for t in srcs) + sum(int(t.shape[3]) for t in shortcut)
-    _call("ladi_conv2d_bf16", 2.0 * n * h_out * w_out * c_out * k_true, C.byref(d), _stream())
+    _call("ladi_conv2d_bf16", 2.0 * n * h_out * w_out * c_out * k_true, C.byref(d), _stream(),
+          tag=f"k{ksize}s{stride} M={n * h_out * w_out} N={c_out} K={k_true} act={act}")
     return out
 
 
@@ -130,7 +131,7 @@ def attention(q, k, v, heads, scale, out=None):
     d.v, d.v_pitch, d.v_batch_stride = v.data_ptr(), v.stride(1), v.stride(0)
     d.out, d.out_pitch, d.out_batch_stride = out.data_ptr(), out.stride(1), out.stride(0)
     d.scale = scale
-    _call("ladi_attention_bf16", 4.0 * B * heads * nq * nkv * 64, C.byref(d), _stream())
+    _call("ladi_attention_bf16", 4.0 * B * heads * nq * nkv * 64, C.byref(d), _stream(), tag=f"B={B} heads={heads} nq={nq} nkv={nkv}")
     return out
 
 
@@ -160,8 +161,8 @@ def groupnorm(srcs, gamma, beta, groups, eps, ws, silu=False, add=None, out=None
         out = torch.empty((n, h, w, c0 + c1), dtype=torch.bfloat16, device=x0.device)
     wsb = ws.get(n, h * w, groups)
     s = _stream()
-    _call("ladi_groupnorm_stats", 0.0, _ptr(x0), c0, p0, _ptr(x1), c1, p1, n, h * w, groups, _ptr(wsb), s)
-    _call("ladi_groupnorm_apply", 0.0, _ptr(x0), c0, p0, _ptr(x1), c1, p1, n, h * w, groups, _ptr(wsb), _ptr(gamma), _ptr(beta),
+    _call("ladi_groupnorm_stats", 2.0 * n * h * w * (c0 + c1), _ptr(x0), c0, p0, _ptr(x1), c1, p1, n, h * w, groups, _ptr(wsb), s)
+    _call("ladi_groupnorm_apply", 4.0 * n * h * w * (c0 + c1), _ptr(x0), c0, p0, _ptr(x1), c1, p1, n, h * w, groups, _ptr(wsb), _ptr(gamma), _ptr(beta),
              eps, int(silu), _ptr(add), (add.stride(2) if add is not None else 0), _ptr(out), out.stride(2), s)
     return out
 

@@ -1,8 +1,11 @@
 """GPU parity of the assembled models and of the whole try-on pipeline against the fp32 CPU oracle (oracle/ladi_oracle),
 same seeded weights and inputs.  The engine computes in bf16 (fp32 accumulate, fp32 latents/scheduler); the stated
 tolerances are on the relative L2 error  |y - ref|_2 / |ref|_2 :
-    single UNet forward        <= 2e-2      VAE moments / decode        <= 2e-2
-    EMASC features             <= 1.5e-2    final image (few DDIM steps) mean |diff| <= 2/255 (small config), reported for full size
+    single UNet forward        <= 2e-2      VAE moments / encoder skips  <= 2e-2
+    EMASC features             <= 1.5e-2    final image (few DDIM steps) mean |diff| <= 2/255 (small config)
+    VAE decode (30 convs deep, small-magnitude output): <= 1.5 x the error of the SAME oracle module executed in bf16 by
+    stock PyTorch library kernels on the GPU ("what a straight port would get", SURVEY.md section 8(c) second tier), cap 5e-2.
+Two engine runs with the same seed must be bit-identical (no floating-point atomics anywhere on the path).
 """
 import numpy as np
 import pytest
@@ -66,7 +69,13 @@ def test_vae_emasc_small(cuda, small):
     for a, b in zip(inter, inter_ref):
         assert rel_l2(a.permute(0, 3, 1, 2), b) < 1.5e-2
     img = pipe.vae.decode(z.to(cuda), inter, [1, 2, 3, 4, 5]).sample
-    assert rel_l2(img, img_ref) < 2e-2
+    import copy
+    ov_bf = copy.deepcopy(ov).to(cuda).bfloat16()
+    with torch.no_grad():
+        port = ov_bf.decode(z.to(cuda).bfloat16(), [t.to(cuda).bfloat16() for t in inter_ref], [1, 2, 3, 4, 5]).sample
+    e_port, e_engine = rel_l2(port, img_ref), rel_l2(img, img_ref)
+    print(f"VAE decode rel-L2 vs fp32 oracle: engine {e_engine:.4f}, bf16 library port {e_port:.4f}")
+    assert e_engine < min(5e-2, 1.5 * e_port)
 
 
 @pytest.mark.parametrize("gs,graph", [(7.5, True), (1.0, True), (7.5, False)])
@@ -87,12 +96,13 @@ def test_pipeline_small(cuda, small, gs, graph):
                guidance_scale=gs, generator=torch.Generator().manual_seed(7), output_type="np").images
     assert out.shape == ref.shape == (2, 128, 64, 3)
     assert np.abs(out - ref).mean() < 2.0 / 255
-    # second call re-uses the captured graph and must reproduce the first bit-for-bit... up to fp32 atomics in GroupNorm
+    print(f"pipeline gs={gs} graph={graph}: mean|engine-oracle| = {np.abs(out - ref).mean() * 255:.3f}/255")
+    # second call re-uses the captured graph and must reproduce the first bit-for-bit
     out2 = pipe(image=inp["image"].clone(), mask_image=inp["mask_image"].clone(), pose_map=inp["pose_map"],
                 warped_cloth=inp["warped_cloth"], prompt_embeds=inp["prompt_embeds"],
                 negative_prompt_embeds=inp["negative_prompt_embeds"], height=128, width=64, num_inference_steps=5,
                 guidance_scale=gs, generator=torch.Generator().manual_seed(7), output_type="np").images
-    assert np.abs(out2 - out).mean() < 0.5 / 255
+    assert np.array_equal(out2, out)
 
 
 def test_pipeline_errors(cuda, small):

@@ -91,9 +91,11 @@ def cpu_reference_sample(args):
     cfg = args.guidance > 1.0
     H, W = args.height, args.width
     with torch.no_grad():
-        ou = OU().eval(); ou.load_state_dict(S.random_state_dict(unet_param_shapes({}), 1234))
-        ov = OV().eval(); ov.load_state_dict(S.random_state_dict(vae_param_shapes({}), 1235))
-        oe = EMASC(S.EMASC_IN, S.EMASC_OUT).eval(); oe.load_state_dict(S.random_state_dict(S.emasc_param_shapes(S.EMASC_IN, S.EMASC_OUT), 1236))
+        with torch.device("meta"):  # skip nn.Module default init of 950 M parameters; weights are assigned below
+            ou, ov, oe = OU().eval(), OV().eval(), EMASC(S.EMASC_IN, S.EMASC_OUT).eval()
+        ou.load_state_dict(S.random_state_dict(unet_param_shapes({}), 1234, fast=True), assign=True)
+        ov.load_state_dict(S.random_state_dict(vae_param_shapes({}), 1235, fast=True), assign=True)
+        oe.load_state_dict(S.random_state_dict(S.emasc_param_shapes(S.EMASC_IN, S.EMASC_OUT), 1236), assign=True)
         inp = S.synthetic_inputs(1, H, W)
         bp = 2 if cfg else 1
         x = torch.randn(bp, 31, H // 8, W // 8)
@@ -176,7 +178,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     cfg = args.guidance > 1.0
     B, H, W = args.batch, args.height, args.width
-    pipe, _ = S.build_pipeline(dev)  # full-size random-init UNet (865,988,484 params) / VAE / EMASC
+    pipe, _ = S.build_pipeline(dev, weights_on_device=True)  # full-size random-init UNet (865,988,484 params) / VAE / EMASC
     host = S.synthetic_inputs(B, H, W, seed=1234 + rank)
     pinned = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}

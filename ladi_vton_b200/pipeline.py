@@ -185,7 +185,10 @@ class StableDiffusionTryOnePipeline:
                  num_inference_steps: int = 50, guidance_scale: float = 7.5, negative_prompt=None, num_images_per_prompt=1,
                  eta: float = 0.0, prompt_embeds=None, negative_prompt_embeds=None, generator=None, latents=None,
                  output_type="pil", return_dict: bool = True, callback=None, callback_steps=1, cloth_cond_rate: float = 1.0,
-                 no_pose: bool = False, cloth_input_type: str = "warped"):
+                 no_pose: bool = False, cloth_input_type: str = "warped", noise=None):
+        """Same arguments as the reference `__call__` (tryon_pipe.py:495-520).  Extensions: output_type="pt" returns the
+        device tensor; `noise=(cloth, latents, masked)` supplies the three RNG draws explicitly (batch-sharded runs slice
+        one full-batch draw, distributed.draw_noise)."""
         dev = self.device
         if dev.type != "cuda":
             raise RuntimeError("call .to('cuda') first: ladi_vton_b200 has no CPU path")
@@ -234,20 +237,20 @@ class StableDiffusionTryOnePipeline:
         # 4b. warped cloth latents (RNG draw #1)
         if cloth_input_type == "warped":
             mom, _ = self.vae.encode_nhwc(warped_cloth)
-            cloth = ops.posterior_sample(mom, _randn((B, 4, h, w), generator, dev), sf)
+            cloth = ops.posterior_sample(mom, noise[0].to(dev) if noise is not None else _randn((B, 4, h, w), generator, dev), sf)
             ops.nchw_to_nhwc(cloth, cond, c_off=c_cloth)
         # 5. timesteps, 6. latents (RNG draw #2)
         self.scheduler.set_timesteps(num_inference_steps, device=dev)
         ts = self.scheduler.timesteps_host
         cloth_steps = (1 - cloth_cond_rate) * num_inference_steps
         if latents is None:
-            latents = _randn((B, 4, h, w), generator, dev)
+            latents = noise[1] if noise is not None else _randn((B, 4, h, w), generator, dev)
         s.latents.copy_(latents.to(dev, torch.float32) * self.scheduler.init_noise_sigma)
         # 7. masked image -> latents + encoder skips (RNG draw #3); EMASC with mask_features fused
         masked = torch.zeros((B, height, width, 8), dtype=torch.bfloat16, device=dev)
         ops.nchw_to_nhwc(image_d, masked, gate=mask_d)  # image * (mask < 0.5)
         mom, feats = self.vae.encode_nhwc(masked, nhwc=True)
-        masked_lat = ops.posterior_sample(mom, _randn((B, 4, h, w), generator, dev), sf)
+        masked_lat = ops.posterior_sample(mom, noise[2].to(dev) if noise is not None else _randn((B, 4, h, w), generator, dev), sf)
         inter = None
         if self.emasc:
             sel = [feats[i] for i in self.emasc_int_layers]  # :460-461

@@ -25,25 +25,31 @@ def emasc_param_shapes(cin, cout):
     return S
 
 
-def random_state_dict(shapes, seed):
+def random_state_dict(shapes, seed, device="cpu", fast=False):
     """PyTorch-default-like init (U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for conv/linear weights and biases, ones/zeros for
-    norms), drawn from one seeded CPU generator in key order."""
-    g = torch.Generator().manual_seed(seed)
+    norms), drawn in key order from one seeded generator on `device` (CPU draws are reproducible across machines and are
+    what the parity tests share between oracle and engine; bench.py draws on the GPU to skip the host cost)."""
+    g = torch.Generator(device=device).manual_seed(seed)
     sd = {}
     fan = {}
+    block = torch.empty(1 << 22, device=device).uniform_(-1.0, 1.0, generator=g) if fast else None
     for k, shp in shapes.items():
         base = k.rsplit(".", 1)[0]
         leaf = base.rsplit(".", 1)[-1]
         is_norm = leaf.startswith("norm") or leaf in ("group_norm", "conv_norm_out", "layer_norm1", "layer_norm2", "post_layernorm")
         if is_norm:
-            sd[k] = torch.ones(shp) if k.endswith("weight") else torch.zeros(shp)
+            sd[k] = torch.ones(shp, device=device) if k.endswith("weight") else torch.zeros(shp, device=device)
             continue
         if k.endswith("weight"):
             fan[base] = math.prod(shp[1:])
             bound = 1.0 / math.sqrt(fan[base])
         else:
             bound = 1.0 / math.sqrt(fan.get(base, shp[0]))
-        sd[k] = (torch.rand(shp, generator=g) * 2 - 1) * bound
+        if fast:  # timing-only weights (CPU baseline legs): tile one random block instead of drawing ~1e9 values
+            n = math.prod(shp)
+            sd[k] = (block.repeat((n + block.numel() - 1) // block.numel())[:n] * bound).reshape(shp)
+        else:
+            sd[k] = torch.empty(shp, device=device).uniform_(-bound, bound, generator=g)
     return sd
 
 
@@ -68,21 +74,21 @@ SMALL_UNET = dict(block_out_channels=(64, 128, 256, 256), attention_head_dim=(1,
 SMALL_VAE = dict(block_out_channels=(64, 128, 256, 256))
 
 
-def build_state_dicts(unet_cfg=None, vae_cfg=None, seed=1234):
+def build_state_dicts(unet_cfg=None, vae_cfg=None, seed=1234, device="cpu"):
     unet_cfg, vae_cfg = unet_cfg or {}, vae_cfg or {}
     from .vae import SD2_VAE
     vch = {**SD2_VAE, **vae_cfg}["block_out_channels"]
     ein, eout = emasc_channels(vch)
-    return dict(unet=random_state_dict(unet_param_shapes(unet_cfg), seed),
-                vae=random_state_dict(vae_param_shapes(vae_cfg), seed + 1),
-                emasc=random_state_dict(emasc_param_shapes(ein, eout), seed + 2),
+    return dict(unet=random_state_dict(unet_param_shapes(unet_cfg), seed, device),
+                vae=random_state_dict(vae_param_shapes(vae_cfg), seed + 1, device),
+                emasc=random_state_dict(emasc_param_shapes(ein, eout), seed + 2, device),
                 emasc_channels=(ein, eout))
 
 
-def build_pipeline(device, unet_cfg=None, vae_cfg=None, seed=1234, sds=None):
+def build_pipeline(device, unet_cfg=None, vae_cfg=None, seed=1234, sds=None, weights_on_device=False):
     """Random-init engine pipeline (the hubconf.py constructors' architectures, no checkpoint)."""
     from . import EMASC, AutoencoderKL, DDIMScheduler, StableDiffusionTryOnePipeline, UNet2DConditionModel
-    sds = sds or build_state_dicts(unet_cfg, vae_cfg, seed)
+    sds = sds or build_state_dicts(unet_cfg, vae_cfg, seed, device if weights_on_device else "cpu")
     unet = UNet2DConditionModel(**(unet_cfg or {})).load_state_dict(sds["unet"])
     vae = AutoencoderKL(**(vae_cfg or {})).load_state_dict(sds["vae"])
     emasc = EMASC(*sds["emasc_channels"]).load_state_dict(sds["emasc"])

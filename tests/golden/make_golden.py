@@ -1,0 +1,65 @@
+"""Generates tests/golden/tryon_small.npz by running the REFERENCE'S OWN FILES -- /root/reference/src/vto_pipelines/
+tryon_pipe.py, src/models/AutoencoderKL.py, src/models/vae.py, src/models/emasc.py, src/utils/data_utils.py, imported
+unmodified -- on the diffusers shim (oracle/shim), CPU fp32, with the seeded small-config weights and synthetic inputs
+that the tests rebuild.  Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+The fixture pins oracle/ladi_oracle (test_oracle_pins.py re-runs the restated oracle against it without /root/reference)
+and is the end-to-end golden vector for the GPU parity tests.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "oracle", "shim"), "/root/reference"):
+    sys.path.insert(0, p)
+
+from ladi_oracle.parts import DDIMScheduler  # noqa: E402
+from ladi_oracle.unet import UNet2DConditionModel  # noqa: E402
+from ladi_vton_b200 import synthetic as S  # noqa: E402
+from src.models.AutoencoderKL import AutoencoderKL as RefVAE  # noqa: E402  (reference file)
+from src.models.emasc import EMASC as RefEMASC  # noqa: E402  (reference file)
+from src.vto_pipelines.tryon_pipe import StableDiffusionTryOnePipeline  # noqa: E402  (reference file)
+
+
+class _TE(torch.nn.Module):  # stand-in exposing .dtype, as read at tryon_pipe.py:255
+    dtype = torch.float32
+
+
+def main():
+    torch.set_num_threads(4)
+    sds = S.build_state_dicts(S.SMALL_UNET, S.SMALL_VAE, seed=1234)
+    unet = UNet2DConditionModel(**S.SMALL_UNET).eval()
+    unet.load_state_dict(sds["unet"])
+    vch = S.SMALL_VAE["block_out_channels"]
+    vae = RefVAE(in_channels=3, out_channels=3, down_block_types=("DownEncoderBlock2D",) * 4, up_block_types=("UpDecoderBlock2D",) * 4,
+                 block_out_channels=vch, layers_per_block=2, latent_channels=4, norm_num_groups=32, sample_size=128).eval()
+    vae.load_state_dict(sds["vae"])
+    emasc = RefEMASC(*sds["emasc_channels"]).eval()
+    emasc.load_state_dict(sds["emasc"])
+    out = {}
+    for tag, gs in (("cfg", 7.5), ("nocfg", 1.0)):
+        inp = S.synthetic_inputs(2, 128, 64, seed=1234, ctx_dim=128)
+        pipe = StableDiffusionTryOnePipeline(vae=vae, text_encoder=_TE(), tokenizer=None, unet=unet, scheduler=DDIMScheduler(),
+                                             emasc=emasc, emasc_int_layers=[1, 2, 3, 4, 5])
+        img = pipe(image=inp["image"], mask_image=inp["mask_image"], pose_map=inp["pose_map"], warped_cloth=inp["warped_cloth"],
+                   prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"], height=128, width=64,
+                   num_inference_steps=3, guidance_scale=gs, generator=torch.Generator().manual_seed(7), output_type="np").images
+        out[f"image_{tag}"] = img.astype(np.float32)
+    # component-level vectors from the reference VAE fork / EMASC
+    with torch.no_grad():
+        x = S.synthetic_inputs(1, 128, 64, seed=99, ctx_dim=128)["image"]
+        enc, feats = vae.encode(x)
+        out["vae_moments"] = enc.latent_dist.parameters.numpy()
+        out["vae_skip3_sub"] = feats[3][:, ::4, ::4, ::4].contiguous().numpy()      # strided subsample keeps the fixture small
+        out["emasc2_sub"] = emasc([f.clone() for f in feats[1:6]])[2][:, ::8, ::4, ::4].contiguous().numpy()
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "tryon_small.npz"), **out)
+    print({k: (v.shape, float(np.abs(v).mean())) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

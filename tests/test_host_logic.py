@@ -1,0 +1,162 @@
+"""CPU tests (-m "not gpu"): the C-ABI library loads and exports every symbol include/ladi_b200.h declares (no compute calls
+without a GPU), weight packing matches the kernel's K-segment walk, host-side pipeline validation, the no-CPU-fallback rule,
+and the N>1 sharding logic over a world_size-2 gloo group."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ladi_vton_b200 import lib
+    hdr = open(os.path.join(ROOT, "include", "ladi_b200.h")).read()
+    declared = set(re.findall(r"LADI_API\s+[\w\s\*]+?\b(ladi_\w+)\s*\(", hdr))
+    assert len(declared) >= 18
+    assert declared == set(lib.SIGNATURES), declared ^ set(lib.SIGNATURES)
+    l = lib.load()  # raises if the .so is missing; getattr raises on a missing export
+    for name in declared:
+        assert hasattr(l, name)
+    assert l.ladi_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (ladi_\w+)", out))
+    assert declared <= exported
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, never fall back to the oracle or to PyTorch ops."""
+    import ladi_vton_b200 as L
+    from ladi_vton_b200 import ops, weights
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError):
+        ops.gemm(torch.zeros(8, 64, dtype=torch.bfloat16), weights.pack_linear(torch.zeros(8, 64)), 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        L.UNet2DConditionModel().to("cpu")
+    src = "".join(open(os.path.join(ROOT, "ladi_vton_b200", f)).read() for f in os.listdir(os.path.join(ROOT, "ladi_vton_b200")) if f.endswith(".py"))
+    assert "ladi_oracle" not in src and "import oracle" not in src  # the product never imports the checker
+
+
+def _emulated_conv(xs, packed, sc=None, stride=1, pad_lo=1, ksize=3):
+    """CPU restatement of ladi_conv2d_bf16's K-segment walk (taps row-major x sources, 64-channel blocks with zero fill,
+    then the 1x1 shortcut segments) -- checks weights.pack_conv against F.conv2d."""
+    n, _, h, w = xs[0].shape
+    ho, wo = ((h + (2 if pad_lo else 1) - 3) // 2 + 1, (w + (2 if pad_lo else 1) - 3) // 2 + 1) if stride == 2 else (h, w)
+    cols = []
+    for ky in range(ksize):
+        for kx in range(ksize):
+            for x in xs:
+                c = x.shape[1]
+                cp = (c + 63) // 64 * 64
+                xp = F.pad(x, (2, 2, 2, 2))
+                oy, ox = (ky - pad_lo, kx - pad_lo) if ksize == 3 else (0, 0)
+                patch = xp[:, :, 2 + oy: 2 + oy + (ho - 1) * stride + 1: stride, 2 + ox: 2 + ox + (wo - 1) * stride + 1: stride]
+                cols.append(F.pad(patch, (0, 0, 0, 0, 0, cp - c)))
+    for x in sc or []:
+        c = x.shape[1]
+        cols.append(F.pad(x, (0, 0, 0, 0, 0, (c + 63) // 64 * 64 - c)))
+    a = torch.cat(cols, dim=1).permute(0, 2, 3, 1).reshape(n * ho * wo, -1)
+    assert a.shape[1] == packed.shape[1]
+    return (a @ packed.float().t()).reshape(n, ho, wo, -1).permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("cs,stride,pad_lo", [([64], 1, 1), ([31], 1, 1), ([128, 64], 1, 1), ([96], 2, 1), ([64], 2, 0)])
+def test_pack_conv_matches_kernel_k_walk(cs, stride, pad_lo):
+    from ladi_vton_b200 import weights
+    g = torch.Generator().manual_seed(0)
+    xs = [torch.randn(2, c, 8, 6, generator=g) for c in cs]
+    w = torch.randn(40, sum(cs), 3, 3, generator=g)
+    packed = weights.pack_conv(w, cs).float()
+    x = torch.cat(xs, 1)
+    ref = F.conv2d(F.pad(x, (0, 1, 0, 1)) if (stride == 2 and pad_lo == 0) else x, w.bfloat16().float(), stride=stride,
+                   padding=0 if (stride == 2 and pad_lo == 0) else 1)
+    got = _emulated_conv(xs, packed, stride=stride, pad_lo=pad_lo)
+    assert got.shape == ref.shape
+    assert torch.allclose(got, ref, atol=1e-3, rtol=1e-3)
+
+
+def test_pack_conv_shortcut_and_geglu_and_linear():
+    from ladi_vton_b200 import weights
+    g = torch.Generator().manual_seed(1)
+    hmid, x0, x1 = torch.randn(1, 64, 4, 4, generator=g), torch.randn(1, 96, 4, 4, generator=g), torch.randn(1, 32, 4, 4, generator=g)
+    w, ws = torch.randn(24, 64, 3, 3, generator=g), torch.randn(24, 128, 1, 1, generator=g)
+    packed = weights.pack_conv(w, [64], ws, [96, 32])
+    assert packed.shape == (24, 9 * 64 + 128 + 64)
+    ref = F.conv2d(hmid, w.bfloat16().float(), padding=1) + F.conv2d(torch.cat([x0, x1], 1), ws.bfloat16().float())
+    assert torch.allclose(_emulated_conv([hmid], packed, sc=[x0, x1]), ref, atol=1e-3, rtol=1e-3)
+    wi, bi = weights.interleave_geglu(torch.arange(8.0)[:, None].repeat(1, 3), torch.arange(8.0))
+    assert bi.tolist() == [0, 4, 1, 5, 2, 6, 3, 7] and wi[:, 0].tolist() == bi.tolist()
+    assert weights.pack_linear(torch.ones(5, 70)).shape == (5, 128)
+
+
+def test_pipeline_host_validation_and_signature():
+    import inspect
+    import ladi_vton_b200 as L
+    sig = inspect.signature(L.StableDiffusionTryOnePipeline.__call__)
+    want = ["self", "image", "mask_image", "pose_map", "warped_cloth", "prompt", "height", "width", "num_inference_steps", "guidance_scale",
+            "negative_prompt", "num_images_per_prompt", "eta", "prompt_embeds", "negative_prompt_embeds", "generator", "latents",
+            "output_type", "return_dict", "callback", "callback_steps", "cloth_cond_rate", "no_pose", "cloth_input_type"]
+    assert list(sig.parameters)[: len(want)] == want  # tryon_pipe.py:495-520
+    d = {k: v.default for k, v in sig.parameters.items()}
+    assert (d["num_inference_steps"], d["guidance_scale"], d["eta"], d["output_type"], d["cloth_cond_rate"], d["cloth_input_type"]) == \
+        (50, 7.5, 0.0, "pil", 1.0, "warped")
+    csig = inspect.signature(L.StableDiffusionTryOnePipeline.__init__)
+    assert list(csig.parameters)[1:] == ["vae", "text_encoder", "tokenizer", "unet", "scheduler", "safety_checker", "feature_extractor",
+                                         "requires_safety_checker", "emasc", "emasc_int_layers"]  # tryon_pipe.py:56-68
+    pipe = L.StableDiffusionTryOnePipeline(vae=L.AutoencoderKL(), text_encoder=None, tokenizer=None, unet=L.UNet2DConditionModel(),
+                                           scheduler=L.DDIMScheduler(), emasc=None, emasc_int_layers=None)
+    assert pipe.vae_scale_factor == 8
+    with pytest.raises(ValueError, match="divisible by 8"):
+        pipe.check_inputs(None, 100, 64, 1, None, torch.zeros(1, 77, 8), None)
+    with pytest.raises(ValueError, match="Cannot forward both"):
+        pipe.check_inputs("a", 64, 64, 1, None, torch.zeros(1, 77, 8), None)
+    with pytest.raises(ValueError, match="callback_steps"):
+        pipe.check_inputs(None, 64, 64, 0, None, torch.zeros(1, 77, 8), None)
+    with pytest.raises(ValueError, match="same shape"):
+        pipe.check_inputs(None, 64, 64, 1, None, torch.zeros(1, 77, 8), torch.zeros(2, 77, 8))
+    m = torch.tensor([[[[0.2, 0.7], [0.5, 0.49]]]])
+    mask, _ = pipe._prepare_mask_and_image(torch.zeros(1, 3, 2, 2), m)
+    assert m.flatten().tolist() == [0.0, 1.0, 1.0, 0.0] and mask is m  # binarised IN PLACE like the reference
+    with pytest.raises(ValueError, match="Image should be"):
+        pipe._prepare_mask_and_image(torch.full((1, 3, 2, 2), 2.0), torch.zeros(1, 1, 2, 2))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pipe.to("cpu")
+    with pytest.raises(RuntimeError, match="state_dict mismatch"):
+        L.EMASC([64], [64]).load_state_dict({"conv.0.0.weight": torch.zeros(1)})
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from ladi_vton_b200 import distributed as D
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    total = 5  # ragged on purpose: 3 + 2
+    inputs = {"image": torch.arange(total * 6, dtype=torch.float32).reshape(total, 1, 2, 3)}
+    mine = D.shard_inputs(inputs, rank, world)
+    noise = D.draw_noise(total, 2, 3, torch.Generator().manual_seed(1234))
+    mynoise = D.shard_noise(noise, rank, world)
+    lo, hi = D.shard_bounds(total, rank, world)
+    ok = torch.equal(mynoise[1], noise[1][lo:hi]) and mine["image"].shape[0] == hi - lo
+    local = mine["image"].permute(0, 2, 3, 1).repeat(1, 1, 1, 3) + mynoise[0][:, :1].permute(0, 2, 3, 1) * 0  # "images" [b,H,W,3]
+    full = D.gather_images(local, world)
+    ok = ok and torch.equal(full, inputs["image"].permute(0, 2, 3, 1).repeat(1, 1, 1, 3))
+    q.put((rank, bool(ok), (lo, hi)))
+    dist.destroy_process_group()
+
+
+def test_sharding_and_gather_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True, (0, 3)), (1, True, (3, 5))]

@@ -1,0 +1,136 @@
+"""CPU tests (-m "not gpu"): the oracle against its pins.
+
+The reference ships no tests or golden vectors, and the arithmetic of its hot path lives in
+diffusers==0.14.0 (not installed, not vendored).  The pins are therefore:
+  1. exact parameter counts of the public SD-2 architectures (865,910,724 / 865,988,484 / 83,653,863 / 7,965,696);
+  2. the state-dict key/shape contract (Appendix A.7) shared by oracle and engine;
+  3. DDIM known answers (timesteps for N=50/20/100, alpha table endpoints);
+  4. tests/golden/tryon_small.npz -- produced by the REFERENCE'S OWN tryon_pipe.py / AutoencoderKL.py / vae.py / emasc.py /
+     data_utils.py running on the diffusers shim in the build container (tests/golden/make_golden.py): the restated oracle
+     must reproduce it (bit-exact where the CPU matches; 1e-4 across machines).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "tryon_small.npz")
+
+
+def _count(m):
+    return sum(p.numel() for p in m.parameters())
+
+
+def test_param_counts_known_answers():
+    from ladi_oracle.parts import EMASC, InversionAdapter
+    from ladi_oracle.unet import UNet2DConditionModel
+    from ladi_oracle.vae import AutoencoderKL
+    with torch.device("meta"):
+        assert _count(UNet2DConditionModel(in_channels=4)) == 865_910_724
+        assert _count(UNet2DConditionModel(in_channels=9)) == 865_925_124
+        assert _count(UNet2DConditionModel()) == 865_988_484
+        assert _count(AutoencoderKL()) == 83_653_863
+        assert _count(EMASC([128, 128, 128, 256, 512], [128, 256, 512, 512, 512])) == 7_965_696
+        assert _count(InversionAdapter()) == 136_360_704
+
+
+def test_state_dict_contract_matches_engine():
+    from ladi_oracle.unet import UNet2DConditionModel
+    from ladi_oracle.vae import AutoencoderKL
+    from ladi_vton_b200 import unet_param_shapes, vae_param_shapes
+    with torch.device("meta"):
+        for mod, shapes in ((UNet2DConditionModel(), unet_param_shapes({})), (AutoencoderKL(), vae_param_shapes({}))):
+            sd = mod.state_dict()
+            assert set(sd) == set(shapes)
+            assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in shapes)
+    assert sum(math.prod(v) for v in unet_param_shapes({}).values()) == 865_988_484
+    for k in ("down_blocks.0.attentions.1.transformer_blocks.0.attn2.to_k.weight", "up_blocks.3.resnets.2.conv_shortcut.weight",
+              "mid_block.attentions.0.proj_out.bias", "time_embedding.linear_2.weight", "up_blocks.2.upsamplers.0.conv.bias"):
+        assert k in unet_param_shapes({})
+    for k in ("encoder.mid_block.attentions.0.query.weight", "decoder.up_blocks.3.resnets.2.conv2.bias", "quant_conv.weight"):
+        assert k in vae_param_shapes({})
+
+
+def test_ddim_known_answers():
+    from ladi_oracle.parts import DDIMScheduler as O
+    from ladi_vton_b200 import DDIMScheduler as E
+    for cls in (O, E):
+        s = cls()
+        s.set_timesteps(50)
+        assert s.timesteps.tolist() == list(range(981, 0, -20))
+        s.set_timesteps(20)
+        assert s.timesteps.tolist() == list(range(951, 0, -50))
+        s.set_timesteps(100)
+        assert s.timesteps[0].item() == 991 and s.timesteps[-1].item() == 1
+        assert abs(s.alphas_cumprod[0].item() - (1 - 0.00085)) < 1e-7
+        assert abs(s.alphas_cumprod[-1].item() - 0.0046602) < 1e-5
+    # engine coefficient table == oracle step arithmetic
+    e, o = E(), O()
+    e.set_timesteps(20); o.set_timesteps(20)
+    coef = e.coefficients()
+    x, eps = torch.randn(1, 4, 8, 6), torch.randn(1, 4, 8, 6)
+    for i, t in enumerate(o.timesteps):
+        ref = o.step(eps, t, x).prev_sample
+        got = coef[i, 2] * ((x - coef[i, 1] * eps) * coef[i, 0]) + coef[i, 3] * eps
+        assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_timestep_embedding_layout():
+    from ladi_oracle.unet import timestep_embedding
+    e = timestep_embedding(torch.tensor([0, 981]), 320)
+    assert e.shape == (2, 320)
+    assert torch.allclose(e[0, :160], torch.ones(160)) and torch.allclose(e[0, 160:], torch.zeros(160))  # [cos, sin]
+    assert abs(e[1, 0].item() - math.cos(981.0)) < 1e-4 and abs(e[1, 160].item() - math.sin(981.0)) < 1e-4
+
+
+def _oracle_small():
+    from ladi_oracle.parts import EMASC, DDIMScheduler
+    from ladi_oracle.pipeline import OracleTryOnPipeline
+    from ladi_oracle.unet import UNet2DConditionModel
+    from ladi_oracle.vae import AutoencoderKL
+    from ladi_vton_b200 import synthetic as S
+    sds = S.build_state_dicts(S.SMALL_UNET, S.SMALL_VAE, seed=1234)
+    ou = UNet2DConditionModel(**S.SMALL_UNET).eval(); ou.load_state_dict(sds["unet"])
+    ov = AutoencoderKL(**S.SMALL_VAE).eval(); ov.load_state_dict(sds["vae"])
+    oe = EMASC(*sds["emasc_channels"]).eval(); oe.load_state_dict(sds["emasc"])
+    return OracleTryOnPipeline(ov, ou, DDIMScheduler(), oe, [1, 2, 3, 4, 5]), ov, oe
+
+
+@pytest.mark.parametrize("tag,gs", [("cfg", 7.5), ("nocfg", 1.0)])
+def test_oracle_reproduces_reference_golden(tag, gs):
+    from ladi_vton_b200 import synthetic as S
+    gold = np.load(GOLD)
+    pipe, _, _ = _oracle_small()
+    inp = S.synthetic_inputs(2, 128, 64, seed=1234, ctx_dim=128)
+    img = pipe(inp["image"], inp["mask_image"], inp["pose_map"], inp["warped_cloth"], inp["prompt_embeds"], inp["negative_prompt_embeds"],
+               height=128, width=64, num_inference_steps=3, guidance_scale=gs, generator=torch.Generator().manual_seed(7))
+    assert img.shape == gold[f"image_{tag}"].shape
+    assert np.abs(img - gold[f"image_{tag}"]).max() < 1e-4
+
+
+def test_oracle_vae_emasc_golden():
+    from ladi_vton_b200 import synthetic as S
+    gold = np.load(GOLD)
+    _, ov, oe = _oracle_small()
+    with torch.no_grad():
+        x = S.synthetic_inputs(1, 128, 64, seed=99, ctx_dim=128)["image"]
+        enc, feats = ov.encode(x)
+        assert np.abs(enc.latent_dist.parameters.numpy() - gold["vae_moments"]).max() < 1e-4
+        assert np.abs(feats[3][:, ::4, ::4, ::4].numpy() - gold["vae_skip3_sub"]).max() < 1e-4
+        e2 = oe(feats[1:6])[2][:, ::8, ::4, ::4].numpy()
+        assert np.abs(e2 - gold["emasc2_sub"]).max() < 1e-4
+    assert len(feats) == 6 and feats[1] is feats[2]  # vae.py:100-109: entries 1 and 2 are the same tensor
+
+
+def test_mask_features_chained_equals_direct():
+    """data_utils.py:9-14 resizes the mask in a chain; the engine uses direct nearest /f -- identical for powers of two."""
+    import torch.nn.functional as F
+    from ladi_oracle.parts import mask_features
+    m = (torch.rand(2, 1, 64, 48) > 0.5).float()
+    feats = [torch.ones(2, 1, 64, 48), torch.ones(2, 1, 64, 48), torch.ones(2, 1, 32, 24), torch.ones(2, 1, 16, 12), torch.ones(2, 1, 8, 6)]
+    out = mask_features(feats, m)
+    for o, f in zip(out, (1, 1, 2, 4, 8)):
+        assert torch.equal(o, 1 - F.interpolate(m, size=(64 // f, 48 // f)))
+        assert torch.equal(o[:, 0], 1 - m[:, 0, ::f, ::f])

@@ -80,6 +80,7 @@ typedef struct ladi_conv_desc {
   int out_pitch;
   int out_fp32;
   int force_bn;              /* 0 = auto; else N tile in {32,64,128,160,192,256} (tests / tuning) */
+  int force_direct_epilogue; /* 1 = direct-store epilogue even where the staged TMA-store epilogue applies (tests) */
 } ladi_conv_desc;
 LADI_API int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream);
 
@@ -94,6 +95,7 @@ typedef struct ladi_attn_desc {
   const void* v; int v_pitch; int64_t v_batch_stride;
   void* out; int out_pitch; int64_t out_batch_stride;
   float scale;               /* softmax(scale * q k^T) */
+  int variant;               /* 0 = auto; 1 = one query tile per CTA; 2 = two query tiles per CTA (tests / tuning) */
 } ladi_attn_desc;
 LADI_API int ladi_attention_bf16(const ladi_attn_desc* d, void* stream);
 

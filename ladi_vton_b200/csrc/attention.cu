@@ -1,12 +1,18 @@
 // Flash-style fused attention for sm_100a, head_dim 64, bf16 in / bf16 out, fp32 softmax state.
-//   S = Q K^T  : tcgen05.mma (M=128 queries, N=128 keys, K=64) into TMEM, double-buffered so QK^T of tile j+1 overlaps
-//                the softmax of tile j;
-//   softmax    : 128 threads, one query row each, read S with tcgen05.ld, online max/sum in the exp2 domain, write P as
-//                bf16 into 128B-swizzled shared memory;
-//   O += P V   : tcgen05.mma with P (K-major, smem) x V (MN-major descriptor straight on the TMA-loaded [keys][64] tile),
-//                O accumulates in TMEM and is rescaled in place (tcgen05.ld/st) only when a row maximum moved.
+//   S = Q K^T  : tcgen05.mma (M=128 queries, N=128 keys, K=64) into TMEM;
+//   softmax    : one thread per query row, S read with tcgen05.ld, online max/sum in the exp2 domain, P written as bf16 into
+//                128B-swizzled shared memory;
+//   O += P V   : tcgen05.mma with P (K-major, smem) x V (MN-major descriptor straight on the TMA-loaded [keys][64] tile); O
+//                accumulates in TMEM and is rescaled in place (tcgen05.ld/st) only when a row maximum moved.
 // Q/K/V tiles arrive by TMA through 3-D tensor maps over [batch][tokens][row pitch], so per-head slices of the fused QKV
 // projection output are read in place (no head split/transposes); out-of-range tokens are zero-filled and masked.
+//
+// Two kernels:
+//   attention_pair_kernel  (nkv > 128): one CTA owns TWO 128-row query tiles with one softmax warpgroup each ("ping-pong"):
+//       the MMA thread interleaves  PV_A(j), S_A(j+1), PV_B(j), S_B(j+1)  so the tensor core works on one tile while the other
+//       tile's warpgroup is in its softmax; K/V tiles are loaded once for both query tiles (2-stage TMA ring).
+//   attention_single_kernel<SHORT>: one query tile per CTA; SHORT (nkv <= 128, e.g. the 77 text tokens of cross-attention)
+//       needs one K/V stage and 256 TMEM columns, so two CTAs share an SM and hide each other's latency chain.
 //
 // Replaces diffusers CrossAttention (attn1/attn2 of BasicTransformerBlock) inside UNet2DConditionModel.forward, which the
 // reference runs through torch SDPA or xformers (/root/reference/src/inference.py:143-147; call-site tryon_pipe.py:732).
@@ -26,15 +32,155 @@ struct AttnParams {
   float scale_log2;  // scale * log2(e)
 };
 
-__global__ void __launch_bounds__(256, 1)
-attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// One query row per thread (128 threads): consumes S tiles from TMEM, produces P tiles in shared memory, keeps O normalised.
+//   S for KV tile j lives at tS + s_stride * (j & s_mask); barriers: s_full (per S buffer), p_full (count 128), o_ready.
+__device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, uint32_t tS, uint32_t s_stride, uint32_t s_mask, uint32_t tO,
+                                             uint8_t* sP, uint32_t s_full0, uint32_t p_full, uint32_t o_ready, int ew, int lane, int q0,
+                                             int h, int b) {
+  const int r = ew * 32 + lane;
+  const uint32_t lane_off = (uint32_t)(ew * 32) << 16;
+  float m = -INFINITY, l = 0.f;
+  uint8_t* prow0 = sP + r * 128;
+  const int sw = r & 7;
+  for (int j = 0; j < n_tiles; ++j) {
+    const uint32_t sb = j & s_mask;
+    const int valid = min(BKV, p.nkv - j * BKV);
+    ptx::mbar_wait(s_full0 + 8 * sb, s_mask ? ((j >> 1) & 1) : (j & 1));
+    ptx::tc_fence_after();
+    const uint32_t ts = tS + sb * s_stride + lane_off;
+    // pass 1: row maximum
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < BKV; c += 32) {
+      if (c >= valid) break;
+      uint32_t v[32];
+      ptx::tmem_ld32(ts + c, v);
+      ptx::tmem_wait_ld();
+      if (c + 32 <= valid) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+    }
+    const float m_new = fmaxf(m, mx * p.scale_log2);
+    const float alpha = ex2(m - m_new);  // 0 on the first tile (m = -inf)
+    // pass 2: p = exp2(s*scale - m_new), packed to bf16
+    uint32_t pk[64];
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < BKV; c += 32) {
+      uint32_t v[32];
+      if (c < valid) {
+        ptx::tmem_ld32(ts + c, v);
+        ptx::tmem_wait_ld();
+      }
+      if (c + 32 <= valid) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
+          const float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_new));
+          sum += p0 + p1;
+          pk[(c + i) >> 1] = ptx::pack_bf16(p0, p1);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = 0.f, p1 = 0.f;
+          if (c + i < valid) p0 = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
+          if (c + i + 1 < valid) p1 = ex2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_new));
+          sum += p0 + p1;
+          pk[(c + i) >> 1] = ptx::pack_bf16(p0, p1);
+        }
+      }
+    }
+    l = l * alpha + sum;
+    const bool moved = m_new > m;
+    m = m_new;
+    // P buffer and O are free once P V of the previous tile has completed
+    if (j > 0) {
+      ptx::mbar_wait(o_ready, (j - 1) & 1);
+      ptx::tc_fence_after();
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {  // 16-byte pieces: 8 per 64-key chunk, XOR-swizzled by (row & 7)
+      uint8_t* dst = prow0 + (q >> 3) * TILE_BYTES + (((q & 7) ^ sw) << 4);
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
+    if (j > 0 && __any_sync(0xffffffffu, moved)) {
+#pragma unroll
+      for (int c = 0; c < HD; c += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tO + lane_off + c, v);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+        ptx::tmem_st32(tO + lane_off + c, v);
+      }
+      ptx::tmem_wait_st();
+    }
+    ptx::tc_fence_before();
+    ptx::fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor core (async proxy)
+    ptx::mbar_arrive(p_full);
+  }
+  // ---- output: O / l
+  ptx::mbar_wait(o_ready, (n_tiles - 1) & 1);
+  ptx::tc_fence_after();
+  const int qi = q0 + r;
+  const float inv = 1.f / l;
+  bf16* orow = p.out + (size_t)b * p.out_batch_stride + (size_t)qi * p.out_pitch + h * HD;
+#pragma unroll
+  for (int c = 0; c < HD; c += 32) {
+    uint32_t v[32];
+    ptx::tmem_ld32(tO + lane_off + c, v);
+    ptx::tmem_wait_ld();
+    if (qi < p.nq) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 u;
+        u.x = ptx::pack_bf16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+        u.y = ptx::pack_bf16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+        u.z = ptx::pack_bf16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+        u.w = ptx::pack_bf16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + c + i) = u;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void issue_qk(uint32_t tS, uint64_t qdesc, uint64_t kdesc) {
+  constexpr uint32_t idesc_qk = ptx::idesc_bf16(128, BKV, 0, 0);
+#pragma unroll
+  for (int k = 0; k < HD / 16; ++k) ptx::mma_ss(tS, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+}
+__device__ __forceinline__ void issue_pv(uint32_t tO, uint64_t pdesc0, uint64_t pdesc1, uint64_t vdesc, int first) {
+  constexpr uint32_t idesc_pv = ptx::idesc_bf16(128, HD, 0, 1);  // B = V is MN-major
+#pragma unroll
+  for (int k = 0; k < BKV / 16; ++k)
+    ptx::mma_ss(tO, (k < 4 ? pdesc0 + 2 * k : pdesc1 + 2 * (k - 4)), vdesc + 128 * k, idesc_pv, (!first) || (k != 0));
+}
+
+// ============================================================================================ one query tile per CTA
+template <bool SHORT>
+__global__ void __launch_bounds__(256, SHORT ? 2 : 1)
+attention_single_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
+  constexpr int KV_STAGES = SHORT ? 1 : 2;
+  constexpr uint32_t TMEM_COLS = SHORT ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + TILE_BYTES;        // 2 stages
-  uint8_t* sV = sK + 2 * TILE_BYTES;    // 2 stages
-  uint8_t* sP = sV + 2 * TILE_BYTES;    // 2 K-chunks of [128][64]
+  uint8_t* sK = sQ + TILE_BYTES;
+  uint8_t* sV = sK + KV_STAGES * TILE_BYTES;
+  uint8_t* sP = sV + KV_STAGES * TILE_BYTES;  // 2 K-chunks of [128][64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * TILE_BYTES);
   const uint32_t b0 = ptx::smem_u32(bars);
   const uint32_t q_full = b0, kv_full0 = b0 + 8, kv_empty0 = b0 + 24, s_full0 = b0 + 40, p_full = b0 + 56, o_ready = b0 + 64;
@@ -56,18 +202,109 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     ptx::mbar_init(o_ready, 1);
     ptx::fence_barrier_init();
   }
+  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), TMEM_COLS);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + (SHORT ? 128 : 256);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(q_full, TILE_BYTES);
+      ptx::tma_load_3d(&tmQ, ptx::smem_u32(sQ), q_full, h * HD, qt * BQ, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = SHORT ? 0 : (j & 1);
+        ptx::mbar_wait(kv_empty0 + 8 * st, ((j >> 1) & 1) ^ 1);
+        const uint32_t fb = kv_full0 + 8 * st;
+        ptx::mbar_expect_tx(fb, 2 * TILE_BYTES);
+        ptx::tma_load_3d(&tmK, ptx::smem_u32(sK + st * TILE_BYTES), fb, h * HD, j * BKV, b);
+        ptx::tma_load_3d(&tmV, ptx::smem_u32(sV + st * TILE_BYTES), fb, h * HD, j * BKV, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint64_t qdesc = ptx::smem_desc_sw128(ptx::smem_u32(sQ));
+      const uint64_t pdesc0 = ptx::smem_desc_sw128(ptx::smem_u32(sP));
+      const uint64_t pdesc1 = ptx::smem_desc_sw128(ptx::smem_u32(sP + TILE_BYTES));
+      ptx::mbar_wait(q_full, 0);
+      for (int j = 0; j <= n_tiles; ++j) {
+        if (j < n_tiles) {
+          const int st = SHORT ? 0 : (j & 1);
+          ptx::mbar_wait(kv_full0 + 8 * st, (j >> 1) & 1);
+          ptx::tc_fence_after();
+          issue_qk(tS + st * BKV, qdesc, ptx::smem_desc_sw128(ptx::smem_u32(sK + st * TILE_BYTES)));
+          ptx::mma_commit(s_full0 + 8 * st);
+        }
+        if (j > 0) {
+          const int i = j - 1, st = SHORT ? 0 : (i & 1);
+          ptx::mbar_wait(p_full, i & 1);
+          ptx::tc_fence_after();
+          issue_pv(tO, pdesc0, pdesc1, ptx::smem_desc_sw128(ptx::smem_u32(sV + st * TILE_BYTES)), i == 0);
+          ptx::mma_commit(kv_empty0 + 8 * st);
+          ptx::mma_commit(o_ready);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // SHORT has a single KV tile, so only S buffer 0 / parity 0 is ever used and the 2-buffer indexing below stays valid
+    softmax_rows(p, n_tiles, tS, BKV, SHORT ? 0u : 1u, tO, sP, s_full0, p_full, o_ready, warp & 3, lane, qt * BQ, h, b);
+  }
+
+  __syncwarp();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ============================================================================================ two query tiles per CTA
+__global__ void __launch_bounds__(384, 1)
+attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                       // 2 query tiles
+  uint8_t* sK = sQ + 2 * TILE_BYTES;        // 2 stages
+  uint8_t* sV = sK + 2 * TILE_BYTES;        // 2 stages
+  uint8_t* sP = sV + 2 * TILE_BYTES;        // 2 query tiles x 2 K-chunks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * TILE_BYTES);
+  const uint32_t b0 = ptx::smem_u32(bars);
+  const uint32_t q_full = b0, kv_full0 = b0 + 8, kv_empty0 = b0 + 24, s_full0 = b0 + 40 /* A: +0, B: +8 */, p_full0 = b0 + 56,
+                 o_ready0 = b0 + 72;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qp = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = p.n_kv_tiles;
+  const bool has_b = (qp * 2 + 1) * BQ < p.nq;  // second query tile holds at least one real row
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(kv_full0 + 8 * s, 1);
+      ptx::mbar_init(kv_empty0 + 8 * s, 1);
+      ptx::mbar_init(s_full0 + 8 * s, 1);
+      ptx::mbar_init(p_full0 + 8 * s, 128);
+      ptx::mbar_init(o_ready0 + 8 * s, 1);
+    }
+    ptx::fence_barrier_init();
+  }
   if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base, tO = tmem_base + 256;
+  // TMEM columns: S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
-      ptx::mbar_expect_tx(q_full, TILE_BYTES);
-      ptx::tma_load_3d(&tmQ, ptx::smem_u32(sQ), q_full, h * HD, qt * BQ, b);
+      ptx::mbar_expect_tx(q_full, (has_b ? 2 : 1) * TILE_BYTES);
+      ptx::tma_load_3d(&tmQ, ptx::smem_u32(sQ), q_full, h * HD, qp * 2 * BQ, b);
+      if (has_b) ptx::tma_load_3d(&tmQ, ptx::smem_u32(sQ + TILE_BYTES), q_full, h * HD, (qp * 2 + 1) * BQ, b);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j & 1;
         ptx::mbar_wait(kv_empty0 + 8 * st, ((j >> 1) & 1) ^ 1);
@@ -79,137 +316,58 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc_qk = ptx::idesc_bf16(128, BKV, 0, 0);
-      constexpr uint32_t idesc_pv = ptx::idesc_bf16(128, HD, 0, 1);  // B = V is MN-major
-      const uint64_t qdesc = ptx::smem_desc_sw128(ptx::smem_u32(sQ));
-      const uint64_t pdesc0 = ptx::smem_desc_sw128(ptx::smem_u32(sP));
-      const uint64_t pdesc1 = ptx::smem_desc_sw128(ptx::smem_u32(sP + TILE_BYTES));
+      const uint64_t qdA = ptx::smem_desc_sw128(ptx::smem_u32(sQ)), qdB = ptx::smem_desc_sw128(ptx::smem_u32(sQ + TILE_BYTES));
+      const uint64_t pA0 = ptx::smem_desc_sw128(ptx::smem_u32(sP)), pA1 = ptx::smem_desc_sw128(ptx::smem_u32(sP + TILE_BYTES));
+      const uint64_t pB0 = ptx::smem_desc_sw128(ptx::smem_u32(sP + 2 * TILE_BYTES)),
+                     pB1 = ptx::smem_desc_sw128(ptx::smem_u32(sP + 3 * TILE_BYTES));
+      const uint32_t tSA = tmem_base, tSB = tmem_base + 128, tOA = tmem_base + 256, tOB = tmem_base + 320;
       ptx::mbar_wait(q_full, 0);
-      for (int j = 0; j <= n_tiles; ++j) {
-        if (j < n_tiles) {
-          const int st = j & 1;
-          ptx::mbar_wait(kv_full0 + 8 * st, (j >> 1) & 1);
-          ptx::tc_fence_after();
-          const uint64_t kdesc = ptx::smem_desc_sw128(ptx::smem_u32(sK + st * TILE_BYTES));
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k) ptx::mma_ss(tS + st * BKV, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
-          ptx::mma_commit(s_full0 + 8 * st);
+      ptx::mbar_wait(kv_full0, 0);
+      ptx::tc_fence_after();
+      {
+        const uint64_t kd = ptx::smem_desc_sw128(ptx::smem_u32(sK));
+        issue_qk(tSA, qdA, kd);
+        ptx::mma_commit(s_full0);
+        if (has_b) {
+          issue_qk(tSB, qdB, kd);
+          ptx::mma_commit(s_full0 + 8);
         }
-        if (j > 0) {
-          const int i = j - 1, st = i & 1;
-          ptx::mbar_wait(p_full, i & 1);
+      }
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1, nst = st ^ 1;
+        const bool more = j + 1 < n_tiles;
+        const uint64_t vd = ptx::smem_desc_sw128(ptx::smem_u32(sV + st * TILE_BYTES));
+        const uint64_t kd_next = ptx::smem_desc_sw128(ptx::smem_u32(sK + nst * TILE_BYTES));
+        // ---- tile A: O_A += P_A(j) V(j); then S_A(j+1) so warpgroup A can start its next softmax at once
+        ptx::mbar_wait(p_full0, j & 1);
+        ptx::tc_fence_after();
+        issue_pv(tOA, pA0, pA1, vd, j == 0);
+        ptx::mma_commit(o_ready0);
+        if (more) {
+          ptx::mbar_wait(kv_full0 + 8 * nst, ((j + 1) >> 1) & 1);
           ptx::tc_fence_after();
-          const uint64_t vdesc = ptx::smem_desc_sw128(ptx::smem_u32(sV + st * TILE_BYTES));
-#pragma unroll
-          for (int k = 0; k < BKV / 16; ++k)
-            ptx::mma_ss(tO, (k < 4 ? pdesc0 + 2 * k : pdesc1 + 2 * (k - 4)), vdesc + 128 * k, idesc_pv, (i | k) != 0);
-          ptx::mma_commit(kv_empty0 + 8 * st);
-          ptx::mma_commit(o_ready);
+          issue_qk(tSA, qdA, kd_next);
+          ptx::mma_commit(s_full0);
+        }
+        // ---- tile B
+        if (has_b) {
+          ptx::mbar_wait(p_full0 + 8, j & 1);
+          ptx::tc_fence_after();
+          issue_pv(tOB, pB0, pB1, vd, j == 0);
+          ptx::mma_commit(o_ready0 + 8);
+        }
+        ptx::mma_commit(kv_empty0 + 8 * st);  // K/V stage j reusable once everything issued so far has completed
+        if (has_b && more) {
+          issue_qk(tSB, qdB, kd_next);
+          ptx::mma_commit(s_full0 + 8);
         }
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ softmax / correction / output (one row per thread)
-    const int ew = warp & 3;
-    const int r = ew * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(ew * 32) << 16;
-    float m = -INFINITY, l = 0.f;
-    uint8_t* prow0 = sP + r * 128;
-    const int sw = r & 7;
-    for (int j = 0; j < n_tiles; ++j) {
-      const int sb = j & 1;
-      const int valid = min(BKV, p.nkv - j * BKV);
-      ptx::mbar_wait(s_full0 + 8 * sb, (j >> 1) & 1);
-      ptx::tc_fence_after();
-      const uint32_t ts = tS + sb * BKV + lane_off;
-      // pass 1: row maximum
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BKV; c += 32) {
-        if (c >= valid) break;
-        uint32_t v[32];
-        ptx::tmem_ld32(ts + c, v);
-        ptx::tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-      }
-      const float m_new = fmaxf(m, mx * p.scale_log2);
-      const float alpha = exp2f(m - m_new);  // 0 on the first tile (m = -inf)
-      // pass 2: p = exp2(s*scale - m_new), packed to bf16
-      uint32_t pk[64];
-      float sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t v[32];
-        if (c < valid) {
-          ptx::tmem_ld32(ts + c, v);
-          ptx::tmem_wait_ld();
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = 0.f, p1 = 0.f;
-          if (c + i < valid) p0 = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
-          if (c + i + 1 < valid) p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_new));
-          // the row sum is taken over the bf16-rounded probabilities that the P V product actually uses
-          const uint32_t u = ptx::pack_bf16(p0, p1);
-          sum += ptx::bf16_lo(u) + ptx::bf16_hi(u);
-          pk[(c + i) >> 1] = u;
-        }
-      }
-      l = l * alpha + sum;
-      const bool moved = m_new > m;
-      m = m_new;
-      // P buffer and O are free once P V of the previous tile has completed
-      if (j > 0) {
-        ptx::mbar_wait(o_ready, (j - 1) & 1);
-        ptx::tc_fence_after();
-      }
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {  // 16-byte pieces: 8 per 64-key chunk, XOR-swizzled by (row & 7)
-        uint8_t* dst = prow0 + (q >> 3) * TILE_BYTES + (((q & 7) ^ sw) << 4);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-      }
-      if (j > 0 && __any_sync(0xffffffffu, moved)) {
-#pragma unroll
-        for (int c = 0; c < HD; c += 32) {
-          uint32_t v[32];
-          ptx::tmem_ld32(tO + lane_off + c, v);
-          ptx::tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-          ptx::tmem_st32(tO + lane_off + c, v);
-        }
-        ptx::tmem_wait_st();
-      }
-      ptx::tc_fence_before();
-      ptx::fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor core (async proxy)
-      ptx::mbar_arrive(p_full);
-    }
-    // ---- output: O / l
-    ptx::mbar_wait(o_ready, (n_tiles - 1) & 1);
-    ptx::tc_fence_after();
-    const int qi = qt * BQ + r;
-    const float inv = 1.f / l;
-    bf16* orow = p.out + (size_t)b * p.out_batch_stride + (size_t)qi * p.out_pitch + h * HD;
-#pragma unroll
-    for (int c = 0; c < HD; c += 32) {
-      uint32_t v[32];
-      ptx::tmem_ld32(tO + lane_off + c, v);
-      ptx::tmem_wait_ld();
-      if (qi < p.nq) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 u;
-          u.x = ptx::pack_bf16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
-          u.y = ptx::pack_bf16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
-          u.z = ptx::pack_bf16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
-          u.w = ptx::pack_bf16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
-          *reinterpret_cast<uint4*>(orow + c + i) = u;
-        }
-      }
-    }
+    const int wg = (warp - 4) >> 2;  // 0 = tile A, 1 = tile B
+    if (wg == 0 || has_b)
+      softmax_rows(p, n_tiles, tmem_base + 128 * wg, 0, 0u, tmem_base + 256 + 64 * wg, sP + wg * 2 * TILE_BYTES, s_full0 + 8 * wg,
+                   p_full0 + 8 * wg, o_ready0 + 8 * wg, warp & 3, lane, (qp * 2 + wg) * BQ, h, b);
   }
 
   __syncwarp();
@@ -221,7 +379,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
-constexpr size_t ATTN_SMEM = 7 * TILE_BYTES + 10 * 8 + 16 + 1024;
+constexpr size_t SMEM_SINGLE = 7 * TILE_BYTES + 10 * 8 + 16 + 1024;
+constexpr size_t SMEM_SHORT = 5 * TILE_BYTES + 10 * 8 + 16 + 1024;
+constexpr size_t SMEM_PAIR = 10 * TILE_BYTES + 12 * 8 + 16 + 1024;
 
 int make_map(CUtensorMap* m, const void* ptr, int cols, int tokens, int batch, int pitch, int64_t batch_stride) {
   const uint64_t dims[3] = {(uint64_t)cols, (uint64_t)tokens, (uint64_t)batch};
@@ -248,11 +408,22 @@ extern "C" int ladi_attention_bf16(const ladi_attn_desc* d, void* stream_) {
   p.scale_log2 = d->scale * 1.4426950408889634f;
   static bool attr_set = false;
   if (!attr_set) {
-    LADI_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATTN_SMEM));
+    LADI_CUDA(cudaFuncSetAttribute(attention_single_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE));
+    LADI_CUDA(cudaFuncSetAttribute(attention_single_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SHORT));
+    LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
     attr_set = true;
   }
-  dim3 grid((d->nq + BQ - 1) / BQ, d->heads, d->batch);
-  attention_kernel<<<grid, 256, ATTN_SMEM, stream>>>(tq, tk, tv, p);
+  const int variant = d->variant;  // 0 auto, 1 single, 2 pair (tests / tuning)
+  if ((variant == 0 && d->nkv <= BKV) || (variant == 1 && d->nkv <= BKV)) {
+    dim3 grid((d->nq + BQ - 1) / BQ, d->heads, d->batch);
+    attention_single_kernel<true><<<grid, 256, SMEM_SHORT, stream>>>(tq, tk, tv, p);
+  } else if (variant == 1) {
+    dim3 grid((d->nq + BQ - 1) / BQ, d->heads, d->batch);
+    attention_single_kernel<false><<<grid, 256, SMEM_SINGLE, stream>>>(tq, tk, tv, p);
+  } else {
+    dim3 grid((d->nq + 2 * BQ - 1) / (2 * BQ), d->heads, d->batch);
+    attention_pair_kernel<<<grid, 384, SMEM_PAIR, stream>>>(tq, tk, tv, p);
+  }
   LADI_CUDA(cudaGetLastError());
   return LADI_OK;
 }

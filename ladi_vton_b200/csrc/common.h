@@ -34,6 +34,6 @@ void ladi_set_error(const char* fmt, ...);
 // Encodes a bf16 tensor map (rank <= 5), SWIZZLE_128B, zero OOB fill.  dims/box innermost first; strides in BYTES for
 // dims 1..rank-1.  Returns 0 on success.
 int ladi_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                          const uint32_t* box);
+                          const uint32_t* box, int swizzle_bytes = 128);
 
 int ladi_num_sms();

@@ -3,6 +3,11 @@
 // scale) -> bf16 or fp32 NHWC.  One persistent CTA per SM; warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
 // allocator, warps 4-7 = epilogue; TMEM accumulator double-buffered so the epilogue of tile i overlaps the MMAs of i+1.
 //
+// Epilogue (bf16 outputs): accumulator slabs of 64 output columns go TMEM -> registers -> 128B-swizzled staging tile in
+// shared memory -> ONE TMA store per slab (hardware clips rows/columns outside the tensor, so ragged tiles need no masks);
+// the residual operand of the same slab is prefetched by TMA into a second staging tile.  Both are double-buffered.
+// fp32 / tiny-N outputs (conv_out, VAE moments, the VAE S matrix) use a direct-store epilogue.
+//
 // Replaces, on the reference hot path: every nn.Conv2d / nn.Linear executed by UNet2DConditionModel.forward
 // (/root/reference/src/vto_pipelines/tryon_pipe.py:732), AutoencoderKL.encode/decode (src/models/vae.py:99-119,183-212) and
 // EMASC.forward (src/models/emasc.py:37-40), which the reference runs as cuDNN/cuBLAS library calls.
@@ -20,6 +25,9 @@ constexpr int BK = 64;    // bf16 channels per K block == one 128-byte swizzle r
 constexpr int UMMA_K = 16;
 constexpr int MAX_SEG = 24;
 constexpr int NUM_A_MAPS = 8;
+constexpr int MAX_STAGES = 8;
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int SLAB_BYTES = BM * 128;  // staging tile: 128 rows x 64 bf16
 
 struct Segment {       // one run of K blocks read from one tensor map with one spatial shift
   int16_t map, dx, dy, chunks;
@@ -32,6 +40,8 @@ struct KParams {
   int tiles_x, tiles_y, tiles_b, tiles_m, tiles_n;
   int c_out;
   int nseg, total_kb;
+  int stages;                 // smem pipeline depth (runtime: whatever fits beside the staging tiles)
+  int staged;                 // 1 = smem-staged TMA-store epilogue (bf16 out), 0 = direct stores
   Segment seg[MAX_SEG];
   const float* bias;          // [c_out] fp32 (per column) or [M] (per row) or null
   int bias_per_row;
@@ -49,30 +59,56 @@ struct KParams {
 struct AMaps {
   CUtensorMap m[NUM_A_MAPS];
 };
+struct EMaps {            // epilogue tensor maps: 64-column (SWIZZLE_128B) and 32-column (SWIZZLE_64B) boxes
+  CUtensorMap out64, out32, res64, res32;
+};
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
-template <int BN, int STAGES>
+struct TileCoord {
+  int nt, x0, y0, n0;
+};
+__device__ __forceinline__ TileCoord tile_coord(const KParams& p, int tile) {
+  TileCoord t;
+  const int mt = tile / p.tiles_n;
+  t.nt = tile - mt * p.tiles_n;
+  const int tb = mt / (p.tiles_y * p.tiles_x);
+  const int rem = mt - tb * (p.tiles_y * p.tiles_x);
+  const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+  t.x0 = tx * p.bw; t.y0 = ty * p.bh; t.n0 = tb * p.bn;
+  return t;
+}
+
+template <int BN>
 __global__ void __launch_bounds__(256, 1)
-convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ KParams p) {
+convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ EMaps emaps,
+                const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int A_BYTES = BM * BK * 2;
   constexpr int B_BYTES = BN * BK * 2;
   constexpr uint32_t ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns per accumulator
   constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
+  const int STAGES = p.stages;
   uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
-  const uint32_t full0 = ptx::smem_u32(bars), empty0 = full0 + 8 * STAGES, tfull0 = empty0 + 8 * STAGES, tempty0 = tfull0 + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint8_t* sB = sA + STAGES * A_BYTES;
+  uint8_t* sOut = sB + STAGES * B_BYTES;                         // 2 staging tiles (staged epilogue only)
+  uint8_t* sRes = sOut + (p.staged ? 2 * SLAB_BYTES : 0);        // 2 residual tiles (staged + residual only)
+  uint8_t* sEnd = sRes + ((p.staged && p.residual != nullptr) ? 2 * SLAB_BYTES : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEnd);
+  const uint32_t full0 = ptx::smem_u32(bars), empty0 = full0 + 8 * MAX_STAGES, tfull0 = empty0 + 8 * MAX_STAGES,
+                 tempty0 = tfull0 + 16, rfull0 = tempty0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 6);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) ptx::prefetch_tmap(&amaps.m[p.seg[s].map]);
     ptx::prefetch_tmap(&tmB);
+    if (p.staged) {
+      ptx::prefetch_tmap(&emaps.out64);
+      if (p.residual != nullptr) ptx::prefetch_tmap(&emaps.res64);
+    }
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(full0 + 8 * s, 1);
       ptx::mbar_init(empty0 + 8 * s, 1);
@@ -80,6 +116,7 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull0 + 8 * a, 1);
       ptx::mbar_init(tempty0 + 8 * a, 128);
+      ptx::mbar_init(rfull0 + 8 * a, 1);
     }
     ptx::fence_barrier_init();
   }
@@ -96,11 +133,7 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
       // ------------------------------------------------------------------ TMA producer
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
-        const int tb = mt / (p.tiles_y * p.tiles_x);
-        const int rem = mt - tb * (p.tiles_y * p.tiles_x);
-        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-        const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = tb * p.bn;
+        const TileCoord tc = tile_coord(p, tile);
         int kb = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const Segment sg = p.seg[s];
@@ -109,9 +142,9 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
             ptx::mbar_wait(empty0 + 8 * stage, phase ^ 1);
             const uint32_t fb = full0 + 8 * stage;
             ptx::mbar_expect_tx(fb, A_BYTES + B_BYTES);
-            ptx::tma_load_4d(am, ptx::smem_u32(sA + stage * A_BYTES), fb, sg.c_begin + c * BK, x0 + sg.dx, y0 + sg.dy, n0);
-            ptx::tma_load_2d(&tmB, ptx::smem_u32(sB + stage * B_BYTES), fb, kb * BK, nt * BN);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            ptx::tma_load_4d(am, ptx::smem_u32(sA + stage * A_BYTES), fb, sg.c_begin + c * BK, tc.x0 + sg.dx, tc.y0 + sg.dy, tc.n0);
+            ptx::tma_load_2d(&tmB, ptx::smem_u32(sB + stage * B_BYTES), fb, kb * BK, tc.nt * BN);
+            if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -136,7 +169,7 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
           for (int k = 0; k < BK / UMMA_K; ++k)
             ptx::mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           ptx::mma_commit(empty0 + 8 * stage);  // smem slot reusable once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
         }
         ptx::mma_commit(tfull0 + 8 * as);  // accumulator complete
       }
@@ -147,112 +180,219 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
     const int r = ew * 32 + lane;
     const float* bias = p.bias;
     if (bias != nullptr && p.step_ptr != nullptr) bias += (size_t)(*p.step_ptr) * p.bias_step_stride;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-      const int mt = tile / p.tiles_n, nt = tile - mt * p.tiles_n;
-      const int tb = mt / (p.tiles_y * p.tiles_x);
-      const int rem = mt - tb * (p.tiles_y * p.tiles_x);
-      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      const int rn = r / (p.bh * p.bw), rr = r - rn * (p.bh * p.bw);
-      const int ry = rr / p.bw, rx = rr - ry * p.bw;
-      const int n = tb * p.bn + rn, y = ty * p.bh + ry, x = tx * p.bw + rx;
-      const bool row_ok = (n < p.n_img) && (y < p.H) && (x < p.W);
-      const size_t grow = ((size_t)n * p.H + y) * p.W + x;
-      const float rscale = (p.row_scale != nullptr && row_ok) ? p.row_scale[grow] : 1.f;
-      const float rbias = (p.bias_per_row && bias != nullptr && row_ok) ? bias[grow] : 0.f;
+    const int rn = r / (p.bh * p.bw), rr = r - rn * (p.bh * p.bw);
+    const int ry = rr / p.bw, rx = rr - ry * p.bw;
 
-      ptx::mbar_wait(tfull0 + 8 * as, aphase);
-      ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + as * ACC_STRIDE + ((uint32_t)(ew * 32) << 16);
+    if (p.staged) {
+      // ================= staged epilogue: TMEM -> regs -> swizzled smem slab -> TMA store; residual slabs by TMA load ============
+      const bool elected = (threadIdx.x == 128);
+      const bool has_res = p.residual != nullptr;
+      const int geglu = p.act == 2;
+      constexpr int BNo_full = BN;                       // accumulator columns per tile
+      const int acc_per_slab = geglu ? 128 : 64;          // accumulator columns feeding one 64-column output slab
+      const int c_eff = geglu ? p.c_out / 2 : p.c_out;    // output channels
+      uint32_t rcount = 0;                                // residual loads issued so far (buffer = rcount & 1)
+      uint32_t scount = 0;                                // slabs processed so far (staging buffer = scount & 1)
+      const int sw128 = r & 7, sw64 = (r >> 1) & 3;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+        const TileCoord tc = tile_coord(p, tile);
+        const int acc0 = tc.nt * BN;                                  // first accumulator column of this tile (global)
+        const int acc_valid = min(BNo_full, p.c_out - acc0);
+        const int nslabs = (acc_valid + acc_per_slab - 1) / acc_per_slab;
+        const int out0 = geglu ? acc0 / 2 : acc0;                     // first output column of this tile
+        const int BNo = geglu ? BN / 2 : BN;                          // output columns per tile
+        const int n = tc.n0 + rn, y = tc.y0 + ry, x = tc.x0 + rx;
+        const bool row_ok = (n < p.n_img) && (y < p.H) && (x < p.W);
+        const size_t grow = ((size_t)n * p.H + y) * p.W + x;
+        const float rscale = (p.row_scale != nullptr && row_ok) ? p.row_scale[grow] : 1.f;
+        const float rbias = (p.bias_per_row && bias != nullptr && row_ok) ? bias[grow] : 0.f;
+
+        if (has_res && elected) {  // residual slab 0 of this tile: issued before waiting for the accumulator
+          const int w0 = min(64, BNo);
+          const uint32_t rb = rfull0 + 8 * (rcount & 1);
+          ptx::mbar_expect_tx(rb, BM * w0 * 2);
+          ptx::tma_load_4d(w0 == 64 ? &emaps.res64 : &emaps.res32, ptx::smem_u32(sRes + (rcount & 1) * SLAB_BYTES), rb, out0, tc.x0, tc.y0,
+                           tc.n0);
+        }
+        ptx::mbar_wait(tfull0 + 8 * as, aphase);
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + as * ACC_STRIDE + ((uint32_t)(ew * 32) << 16);
+
+        for (int s = 0; s < nslabs; ++s, ++scount) {
+          const int wout = min(64, BNo - 64 * s);                    // 64, or 32 for the tail slab of BN=160/32 tiles
+          const int ocol = out0 + 64 * s;                            // first output column of the slab (global)
+          const uint32_t rbuf = rcount & 1;
+          if (has_res) {
+            if (elected && s + 1 < nslabs) {                          // prefetch the next residual slab into the other buffer
+              const int w1 = min(64, BNo - 64 * (s + 1));
+              const uint32_t rb = rfull0 + 8 * ((rcount + 1) & 1);
+              ptx::mbar_expect_tx(rb, BM * w1 * 2);
+              ptx::tma_load_4d(w1 == 64 ? &emaps.res64 : &emaps.res32, ptx::smem_u32(sRes + ((rcount + 1) & 1) * SLAB_BYTES), rb,
+                               ocol + 64, tc.x0, tc.y0, tc.n0);
+            }
+            ptx::mbar_wait(rfull0 + 8 * rbuf, (rcount >> 1) & 1);
+          }
+          uint8_t* ostage = sOut + (scount & 1) * SLAB_BYTES;
+          const uint8_t* rstage = sRes + rbuf * SLAB_BYTES;
+          // ---- 64 output columns = 2 (or, GEGLU, 4) accumulator chunks of 32
+          const int nchunks = geglu ? (wout * 2) / 32 : wout / 32;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        const int col0 = nt * BN + c0;
-        if (col0 >= p.c_out) break;  // uniform across the CTA
-        uint32_t v[32];
-        ptx::tmem_ld32(t_row + c0, v);
-        ptx::tmem_wait_ld();
-        if (!row_ok) continue;
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        const int ncols = min(32, p.c_out - col0);
-        if (bias != nullptr) {
-          if (p.bias_per_row) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += rbias;
-          } else if (ncols == 32) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
-              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+          for (int c = 0; c < nchunks; ++c) {
+            const int acol = (geglu ? 128 : 64) * s + 32 * c;       // accumulator column within the tile
+            uint32_t v[32];
+            ptx::tmem_ld32(t_row + acol, v);
+            ptx::tmem_wait_ld();
+            if (s == nslabs - 1 && c == nchunks - 1) {               // accumulator fully read: hand it back to the MMA warp
+              ptx::tc_fence_before();
+              ptx::mbar_arrive(tempty0 + 8 * as);
             }
-          } else {
+            float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) f[j] += __ldg(bias + col0 + j);
-          }
-        }
-        if (p.act == 2) {
-          // GEGLU: interleaved (value, gate) column pairs -> 16 outputs per 32 accumulator columns
-          bf16* orow = reinterpret_cast<bf16*>(p.out) + grow * p.out_pitch + (col0 >> 1);
-          uint32_t o[8];
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            const int gcol = acc0 + acol;                            // global accumulator column (bias index)
+            if (bias != nullptr) {
+              if (p.bias_per_row) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            o[j] = ptx::pack_bf16(f[4 * j] * gelu_erf(f[4 * j + 1]), f[4 * j + 2] * gelu_erf(f[4 * j + 3]));
-          if (ncols == 32) {
-            reinterpret_cast<uint4*>(orow)[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            reinterpret_cast<uint4*>(orow)[1] = make_uint4(o[4], o[5], o[6], o[7]);
-          } else {
-            for (int j = 0; j < ncols / 2; ++j) orow[j] = __float2bfloat16(f[2 * j] * gelu_erf(f[2 * j + 1]));
-          }
-          continue;
-        }
-        if (p.act == 1) {
+                for (int j = 0; j < 32; ++j) f[j] += rbias;
+              } else if (gcol + 32 <= p.c_out) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
-        }
-        if (p.residual != nullptr) {
-          const bf16* rrow = p.residual + grow * p.residual_pitch + col0;
-          if (ncols == 32) {
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + gcol + j));
+                  f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                }
+              } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint4 u = __ldg(reinterpret_cast<const uint4*>(rrow + j));
-              f[j] += ptx::bf16_lo(u.x); f[j + 1] += ptx::bf16_hi(u.x);
-              f[j + 2] += ptx::bf16_lo(u.y); f[j + 3] += ptx::bf16_hi(u.y);
-              f[j + 4] += ptx::bf16_lo(u.z); f[j + 5] += ptx::bf16_hi(u.z);
-              f[j + 6] += ptx::bf16_lo(u.w); f[j + 7] += ptx::bf16_hi(u.w);
+                for (int j = 0; j < 32; ++j)
+                  if (gcol + j < p.c_out) f[j] += __ldg(bias + gcol + j);
+              }
             }
-          } else {
-            for (int j = 0; j < ncols; ++j) f[j] += __bfloat162float(rrow[j]);
+            if (geglu) {
+              // 32 accumulator columns -> 16 outputs = 2 pieces of 16 bytes at output columns 16c .. 16c+15 of the slab
+              uint32_t o[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                o[j] = ptx::pack_bf16(f[4 * j] * gelu_erf(f[4 * j + 1]) * rscale, f[4 * j + 2] * gelu_erf(f[4 * j + 3]) * rscale);
+              const int q0 = 2 * c;                                  // 16-byte piece index within the 128-byte row
+              *reinterpret_cast<uint4*>(ostage + r * 128 + (((q0) ^ sw128) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(ostage + r * 128 + (((q0 + 1) ^ sw128) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+              continue;
+            }
+            if (p.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {                            // 4 pieces of 8 columns (16 bytes of bf16)
+              const int piece = 4 * c + q;                           // piece index within the slab row
+              const int off = (wout == 64) ? r * 128 + ((piece ^ sw128) << 4) : r * 64 + ((piece ^ sw64) << 4);
+              float* g = f + 8 * q;
+              if (has_res) {
+                const uint4 u = *reinterpret_cast<const uint4*>(rstage + off);
+                g[0] += ptx::bf16_lo(u.x); g[1] += ptx::bf16_hi(u.x); g[2] += ptx::bf16_lo(u.y); g[3] += ptx::bf16_hi(u.y);
+                g[4] += ptx::bf16_lo(u.z); g[5] += ptx::bf16_hi(u.z); g[6] += ptx::bf16_lo(u.w); g[7] += ptx::bf16_hi(u.w);
+              }
+              *reinterpret_cast<uint4*>(ostage + off) =
+                  make_uint4(ptx::pack_bf16(g[0] * rscale, g[1] * rscale), ptx::pack_bf16(g[2] * rscale, g[3] * rscale),
+                             ptx::pack_bf16(g[4] * rscale, g[5] * rscale), ptx::pack_bf16(g[6] * rscale, g[7] * rscale));
+            }
           }
-        }
-        if (p.row_scale != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] *= rscale;
-        }
-        if (p.out_fp32) {
-          float* orow = reinterpret_cast<float*>(p.out) + grow * p.out_pitch + col0;
-          if (ncols == 32 && (p.out_pitch & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(orow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-            for (int j = 0; j < ncols; ++j) orow[j] = f[j];
-          }
-        } else {
-          bf16* orow = reinterpret_cast<bf16*>(p.out) + grow * p.out_pitch + col0;
-          if (ncols == 32 && (p.out_pitch & 7) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              *reinterpret_cast<uint4*>(orow + j) = make_uint4(ptx::pack_bf16(f[j], f[j + 1]), ptx::pack_bf16(f[j + 2], f[j + 3]),
-                                                                 ptx::pack_bf16(f[j + 4], f[j + 5]), ptx::pack_bf16(f[j + 6], f[j + 7]));
-          } else {
-            for (int j = 0; j < ncols; ++j) orow[j] = __float2bfloat16(f[j]);
+          if (has_res) ++rcount;
+          ptx::fence_proxy_async_smem();                 // staging writes -> visible to the TMA engine
+          if (elected) ptx::tma_store_wait_read0();      // the store that used the OTHER staging tile has drained it
+          ptx::named_barrier_sync(1, 128);
+          if (elected && ocol < c_eff) {
+            ptx::tma_store_4d(wout == 64 ? &emaps.out64 : &emaps.out32, ptx::smem_u32(ostage), ocol, tc.x0, tc.y0, tc.n0);
+            ptx::tma_store_commit();
           }
         }
       }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(tempty0 + 8 * as);
+      if (elected) ptx::tma_store_wait_read0();
+    } else {
+      // ================= direct-store epilogue (fp32 outputs, tiny / unaligned N) ==================================================
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+        const TileCoord tc = tile_coord(p, tile);
+        const int nt = tc.nt;
+        const int n = tc.n0 + rn, y = tc.y0 + ry, x = tc.x0 + rx;
+        const bool row_ok = (n < p.n_img) && (y < p.H) && (x < p.W);
+        const size_t grow = ((size_t)n * p.H + y) * p.W + x;
+        const float rscale = (p.row_scale != nullptr && row_ok) ? p.row_scale[grow] : 1.f;
+        const float rbias = (p.bias_per_row && bias != nullptr && row_ok) ? bias[grow] : 0.f;
+
+        ptx::mbar_wait(tfull0 + 8 * as, aphase);
+        ptx::tc_fence_after();
+        const uint32_t t_row = tmem_base + as * ACC_STRIDE + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          const int col0 = nt * BN + c0;
+          if (col0 >= p.c_out) break;  // uniform across the CTA
+          uint32_t v[32];
+          ptx::tmem_ld32(t_row + c0, v);
+          ptx::tmem_wait_ld();
+          if (!row_ok) continue;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          const int ncols = min(32, p.c_out - col0);
+          if (bias != nullptr) {
+            if (p.bias_per_row) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] += rbias;
+            } else if (ncols == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+                f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) f[j] += __ldg(bias + col0 + j);
+            }
+          }
+          if (p.act == 2) {
+            bf16* orow = reinterpret_cast<bf16*>(p.out) + grow * p.out_pitch + (col0 >> 1);
+            for (int j = 0; j < ncols / 2; ++j) orow[j] = __float2bfloat16(f[2 * j] * gelu_erf(f[2 * j + 1]) * rscale);
+            continue;
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = silu_f(f[j]);
+          }
+          if (p.residual != nullptr) {
+            const bf16* rrow = p.residual + grow * p.residual_pitch + col0;
+            for (int j = 0; j < ncols; ++j) f[j] += __bfloat162float(rrow[j]);
+          }
+          if (p.row_scale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= rscale;
+          }
+          if (p.out_fp32) {
+            float* orow = reinterpret_cast<float*>(p.out) + grow * p.out_pitch + col0;
+            if (ncols == 32 && (p.out_pitch & 3) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(orow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+              for (int j = 0; j < ncols; ++j) orow[j] = f[j];
+            }
+          } else {
+            bf16* orow = reinterpret_cast<bf16*>(p.out) + grow * p.out_pitch + col0;
+            if (ncols == 32 && (p.out_pitch & 7) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8)
+                *reinterpret_cast<uint4*>(orow + j) = make_uint4(ptx::pack_bf16(f[j], f[j + 1]), ptx::pack_bf16(f[j + 2], f[j + 3]),
+                                                                   ptx::pack_bf16(f[j + 4], f[j + 5]), ptx::pack_bf16(f[j + 6], f[j + 7]));
+            } else {
+              for (int j = 0; j < ncols; ++j) orow[j] = __float2bfloat16(f[j]);
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(tempty0 + 8 * as);
+      }
     }
   }
 
@@ -265,22 +405,26 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
   }
 }
 
-template <int BN, int STAGES>
-constexpr size_t smem_bytes() {
-  return (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + (2 * STAGES + 4) * 8 + 16 + 1024;
-}
+constexpr size_t SMEM_LIMIT = 232448;  // 227 KiB per CTA
+constexpr size_t SMEM_TAIL = (2 * MAX_STAGES + 6) * 8 + 16 + 1024;  // barriers + TMEM slot + alignment slack
 
-template <int BN, int STAGES>
-int launch(const AMaps& am, const CUtensorMap& tmB, const KParams& kp, cudaStream_t stream) {
+template <int BN>
+int launch(const AMaps& am, const CUtensorMap& tmB, const EMaps& em, KParams& kp, cudaStream_t stream) {
   static bool attr_set = false;
-  constexpr size_t smem = smem_bytes<BN, STAGES>();
   if (!attr_set) {
-    LADI_CUDA(cudaFuncSetAttribute(convgemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LADI_CUDA(cudaFuncSetAttribute(convgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
     attr_set = true;
   }
+  const size_t staging = kp.staged ? (size_t)(kp.residual != nullptr ? 4 : 2) * SLAB_BYTES : 0;
+  const size_t per_stage = A_BYTES + (size_t)BN * BK * 2;
+  int stages = (int)((SMEM_LIMIT - SMEM_TAIL - staging) / per_stage);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  LADI_CHECK(stages >= 2, "not enough shared memory for a 2-stage pipeline");
+  kp.stages = stages;
+  const size_t smem = stages * per_stage + staging + SMEM_TAIL;
   const int tiles = kp.tiles_m * kp.tiles_n;
   const int grid = tiles < ladi_num_sms() ? tiles : ladi_num_sms();
-  convgemm_kernel<BN, STAGES><<<grid, 256, smem, stream>>>(am, tmB, kp);
+  convgemm_kernel<BN><<<grid, 256, smem, stream>>>(am, tmB, em, kp);
   LADI_CUDA(cudaGetLastError());
   return LADI_OK;
 }
@@ -289,6 +433,12 @@ int largest_pow2_divisor(int v, int cap) {
   int d = 1;
   while (d * 2 <= cap && v % (d * 2) == 0) d *= 2;
   return d;
+}
+
+int encode_nhwc_map(CUtensorMap* m, const void* base, int channels, int pitch, int w, int h, int n, const uint32_t* box, int swz) {
+  const uint64_t dims[4] = {(uint64_t)channels, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+  const uint64_t strides[3] = {(uint64_t)pitch * 2, (uint64_t)pitch * 2 * w, (uint64_t)pitch * 2 * w * h};
+  return ladi_encode_tmap_bf16(m, base, 4, dims, strides, box, swz);
 }
 
 }  // namespace
@@ -307,6 +457,7 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
   KParams kp;
   memset(&kp, 0, sizeof(kp));
   AMaps am;
+  EMaps em;
   kp.n_img = d->n; kp.H = d->h_out; kp.W = d->w_out; kp.c_out = d->c_out;
   kp.bw = largest_pow2_divisor(d->w_out, 128);
   if (d->ksize == 1 && d->h_out == 1 && d->stride == 1) kp.bw = 128;  // plain GEMM: row tail handled by OOB fill
@@ -344,10 +495,7 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
     LADI_CHECK(d->sc[i] != nullptr && d->sc_c[i] > 0 && d->sc_pitch[i] % 8 == 0, "shortcut source %d invalid", i);
     LADI_CHECK(nmaps < NUM_A_MAPS, "too many tensor maps");
     sc_map0[i] = nmaps;
-    const uint64_t pitch = (uint64_t)d->sc_pitch[i];
-    const uint64_t dims[4] = {(uint64_t)d->sc_c[i], (uint64_t)d->w_out, (uint64_t)d->h_out, (uint64_t)d->n};
-    const uint64_t strides[3] = {pitch * 2, pitch * 2 * d->w_out, pitch * 2 * (uint64_t)d->w_out * d->h_out};
-    if (ladi_encode_tmap_bf16(&am.m[nmaps], d->sc[i], 4, dims, strides, box)) return LADI_ERR_CUDA;
+    if (encode_nhwc_map(&am.m[nmaps], d->sc[i], d->sc_c[i], d->sc_pitch[i], d->w_out, d->h_out, d->n, box, 128)) return LADI_ERR_CUDA;
     ++nmaps;
   }
   for (int i = nmaps; i < NUM_A_MAPS; ++i) am.m[i] = am.m[0];
@@ -387,6 +535,13 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
   kp.residual = reinterpret_cast<const bf16*>(d->residual); kp.residual_pitch = d->residual_pitch;
   kp.row_scale = d->row_scale; kp.act = d->act; kp.out = d->out; kp.out_pitch = d->out_pitch; kp.out_fp32 = d->out_fp32;
 
+  // ---- epilogue flavour: staged TMA stores need bf16 output with 16-byte aligned rows
+  const int c_eff = d->act == 2 ? d->c_out / 2 : d->c_out;
+  kp.staged = (!d->out_fp32 && d->out_pitch % 8 == 0 && c_eff % 8 == 0 && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 &&
+               (d->residual == nullptr || (d->residual_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(d->residual) & 15) == 0)) &&
+               d->force_direct_epilogue == 0)
+                  ? 1 : 0;
+
   // ---- N tile: minimise (waves x per-tile cost) with per-tile cost ~ BN + fixed A-operand cost
   const int sms = ladi_num_sms();
   int BN = 0;
@@ -396,11 +551,13 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
     static const int cand[6] = {256, 192, 160, 128, 64, 32};
     long best = -1;
     for (int i = 0; i < 6; ++i) {
+      if (d->act == 2 && kp.staged && cand[i] % 128 != 0) continue;  // GEGLU slabs consume 128 accumulator columns
       const long tiles = (long)kp.tiles_m * ((d->c_out + cand[i] - 1) / cand[i]);
       const long cost = ((tiles + sms - 1) / sms) * (cand[i] + 64);
       if (best < 0 || cost < best) { best = cost; BN = cand[i]; }
     }
   }
+  if (d->act == 2 && kp.staged && BN % 128 != 0) kp.staged = 0;
   kp.tiles_n = (d->c_out + BN - 1) / BN;
 
   CUtensorMap tmB;
@@ -410,13 +567,27 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
     const uint32_t bbox[2] = {(uint32_t)BK, (uint32_t)BN};
     if (ladi_encode_tmap_bf16(&tmB, d->weight, 2, dims, strides, bbox)) return LADI_ERR_CUDA;
   }
+  if (kp.staged) {
+    const uint32_t box64[4] = {64u, (uint32_t)kp.bw, (uint32_t)kp.bh, (uint32_t)kp.bn};
+    const uint32_t box32[4] = {32u, (uint32_t)kp.bw, (uint32_t)kp.bh, (uint32_t)kp.bn};
+    if (encode_nhwc_map(&em.out64, d->out, c_eff, d->out_pitch, d->w_out, d->h_out, d->n, box64, 128)) return LADI_ERR_CUDA;
+    if (encode_nhwc_map(&em.out32, d->out, c_eff, d->out_pitch, d->w_out, d->h_out, d->n, box32, 64)) return LADI_ERR_CUDA;
+    if (d->residual != nullptr) {
+      if (encode_nhwc_map(&em.res64, d->residual, c_eff, d->residual_pitch, d->w_out, d->h_out, d->n, box64, 128)) return LADI_ERR_CUDA;
+      if (encode_nhwc_map(&em.res32, d->residual, c_eff, d->residual_pitch, d->w_out, d->h_out, d->n, box32, 64)) return LADI_ERR_CUDA;
+    } else {
+      em.res64 = em.out64; em.res32 = em.out32;
+    }
+  } else {
+    em.out64 = em.out32 = em.res64 = em.res32 = tmB;
+  }
   switch (BN) {
-    case 256: return launch<256, 4>(am, tmB, kp, stream);
-    case 192: return launch<192, 5>(am, tmB, kp, stream);
-    case 160: return launch<160, 5>(am, tmB, kp, stream);
-    case 128: return launch<128, 6>(am, tmB, kp, stream);
-    case 64: return launch<64, 8>(am, tmB, kp, stream);
-    case 32: return launch<32, 8>(am, tmB, kp, stream);
+    case 256: return launch<256>(am, tmB, em, kp, stream);
+    case 192: return launch<192>(am, tmB, em, kp, stream);
+    case 160: return launch<160>(am, tmB, em, kp, stream);
+    case 128: return launch<128>(am, tmB, em, kp, stream);
+    case 64: return launch<64>(am, tmB, em, kp, stream);
+    case 32: return launch<32>(am, tmB, em, kp, stream);
     default: LADI_CHECK(false, "unsupported BN %d", BN);
   }
 }

@@ -78,6 +78,19 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint32_t dst, 
       : "memory");
 }
 
+// TMA stores (shared -> global, bulk async group); out-of-range box elements are clipped by the hardware
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void named_barrier_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------- tcgen05
 // TMEM allocation: executed by ONE full warp; ncols power of two in [32, 512].
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {

@@ -21,7 +21,7 @@ class ConvDesc(C.Structure):
         ("bias", C.c_void_p), ("bias_per_row", C.c_int), ("bias_step_stride", C.c_int), ("step_ptr", C.c_void_p),
         ("residual", C.c_void_p), ("residual_pitch", C.c_int),
         ("row_scale", C.c_void_p), ("act", C.c_int),
-        ("out", C.c_void_p), ("out_pitch", C.c_int), ("out_fp32", C.c_int), ("force_bn", C.c_int),
+        ("out", C.c_void_p), ("out_pitch", C.c_int), ("out_fp32", C.c_int), ("force_bn", C.c_int), ("force_direct_epilogue", C.c_int),
     ]
 
 
@@ -32,7 +32,7 @@ class AttnDesc(C.Structure):
         ("k", C.c_void_p), ("k_pitch", C.c_int), ("k_batch_stride", C.c_int64),
         ("v", C.c_void_p), ("v_pitch", C.c_int), ("v_batch_stride", C.c_int64),
         ("out", C.c_void_p), ("out_pitch", C.c_int), ("out_batch_stride", C.c_int64),
-        ("scale", C.c_float),
+        ("scale", C.c_float), ("variant", C.c_int),
     ]
 
 

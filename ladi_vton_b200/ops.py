@@ -51,7 +51,7 @@ def padded_k(channels):
 
 def conv2d(srcs, weight, c_out, *, ksize=3, stride=1, pad_lo=1, shortcut=(), bias=None, bias_per_row=False,
            bias_step_stride=0, step_ptr=None, residual=None, row_scale=None, act=ACT_NONE, out=None, out_fp32=False,
-           force_bn=0):
+           force_bn=0, direct_epilogue=False):
     """Implicit-GEMM convolution over the channel-concat of `srcs` (+ fused 1x1 over `shortcut` tensors).
     `weight`: packed bf16 [c_out, k_total] (see weights.pack_conv).  Returns the NHWC output tensor."""
     assert 1 <= len(srcs) <= 2 and len(shortcut) <= 2
@@ -95,6 +95,7 @@ def conv2d(srcs, weight, c_out, *, ksize=3, stride=1, pad_lo=1, shortcut=(), bia
         assert row_scale.dtype == torch.float32 and row_scale.numel() == n * h_out * w_out
         d.row_scale = row_scale.data_ptr()
     d.act, d.out, d.out_pitch, d.out_fp32, d.force_bn = act, out.data_ptr(), op, int(out_fp32), force_bn
+    d.force_direct_epilogue = int(direct_epilogue)
     # algorithmic flops: 2 * output pixels * c_out * true reduction length (padding channels excluded)
     k_true = ksize * ksize * sum(int(t.shape[3]) for t in srcs) + sum(int(t.shape[3]) for t in shortcut)
     _call("ladi_conv2d_bf16", 2.0 * n * h_out * w_out * c_out * k_true, C.byref(d), _stream(),
@@ -116,7 +117,7 @@ def gemm(a, weight, n_out, **kw):
     return o[0, 0]
 
 
-def attention(q, k, v, heads, scale, out=None):
+def attention(q, k, v, heads, scale, out=None, variant=0):
     """q [B, Nq, >=heads*64] , k/v [B, Nkv, >=heads*64] (row-strided views of fused projections are fine) -> [B, Nq, heads*64]."""
     B, nq = q.shape[0], q.shape[1]
     nkv = k.shape[1]
@@ -131,6 +132,7 @@ def attention(q, k, v, heads, scale, out=None):
     d.v, d.v_pitch, d.v_batch_stride = v.data_ptr(), v.stride(1), v.stride(0)
     d.out, d.out_pitch, d.out_batch_stride = out.data_ptr(), out.stride(1), out.stride(0)
     d.scale = scale
+    d.variant = variant
     _call("ladi_attention_bf16", 4.0 * B * heads * nq * nkv * 64, C.byref(d), _stream(), tag=f"B={B} heads={heads} nq={nq} nkv={nkv}")
     return out
 

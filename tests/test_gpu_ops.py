@@ -23,22 +23,26 @@ def rnd(shape, dev, seed, scale=1.0):
 @pytest.mark.parametrize("M,K,N,bn", [(512, 320, 320, 0), (200, 64, 96, 0), (384, 1024, 640, 0), (128, 128, 4, 0),
                                       (256, 256, 256, 32), (256, 256, 256, 64), (256, 256, 256, 128), (256, 256, 320, 160),
                                       (256, 256, 384, 192), (256, 256, 512, 256), (3072, 320, 960, 0), (77 * 2, 1024, 640, 0)])
-def test_gemm_plain(cuda, M, K, N, bn):
+@pytest.mark.parametrize("direct", [False, True])
+def test_gemm_plain(cuda, M, K, N, bn, direct):
     from ladi_vton_b200 import ops, weights
     a = rnd((M, K), cuda, 1).bfloat16()
     w = rnd((N, K), cuda, 2, K ** -0.5)
     b = rnd((N,), cuda, 3)
-    y = ops.gemm(a, weights.pack_linear(w), N, bias=b, force_bn=bn)
+    y = ops.gemm(a, weights.pack_linear(w), N, bias=b, force_bn=bn, direct_epilogue=direct)
     ref = a.float() @ w.bfloat16().float().t() + b
     torch.cuda.synchronize()
     assert y.shape == (M, N)
     assert nerr(y, ref) < TOL_BF16
 
 
+@pytest.mark.parametrize("bn", [0, 160, 256])
 @pytest.mark.parametrize("mode", ["residual", "silu", "geglu", "fp32", "rowscale", "rowbias", "stepbias", "strided"])
-def test_gemm_epilogues(cuda, mode):
+def test_gemm_epilogues(cuda, mode, bn):
     from ladi_vton_b200 import ops, weights
     M, K, N = 300, 320, 640
+    if mode == "geglu" and bn == 160:
+        bn = 128
     a = rnd((M, K), cuda, 1).bfloat16()
     w = rnd((N, K), cuda, 2, K ** -0.5)
     b = rnd((N,), cuda, 3)
@@ -46,41 +50,41 @@ def test_gemm_epilogues(cuda, mode):
     base = a.float() @ wb.t() + b
     if mode == "residual":
         r = rnd((M, N), cuda, 4).bfloat16()
-        y = ops.gemm(a, weights.pack_linear(w), N, bias=b, residual=r)
+        y = ops.gemm(a, weights.pack_linear(w), N, bias=b, residual=r, force_bn=bn)
         ref = base + r.float()
     elif mode == "silu":
-        y = ops.gemm(a, weights.pack_linear(w), N, bias=b, act=ops.ACT_SILU)
+        y = ops.gemm(a, weights.pack_linear(w), N, bias=b, act=ops.ACT_SILU, force_bn=bn)
         ref = F.silu(base)
     elif mode == "geglu":
         wi, bi = weights.interleave_geglu(w, b)
-        y = ops.gemm(a, weights.pack_linear(wi), N, bias=bi.contiguous(), act=ops.ACT_GEGLU)
+        y = ops.gemm(a, weights.pack_linear(wi), N, bias=bi.contiguous(), act=ops.ACT_GEGLU, force_bn=bn)
         v, g = base.chunk(2, dim=-1)
         ref = v * F.gelu(g)
         assert y.shape == (M, N // 2)
     elif mode == "fp32":
-        y = ops.gemm(a, weights.pack_linear(w), N, bias=b, out_fp32=True)
+        y = ops.gemm(a, weights.pack_linear(w), N, bias=b, out_fp32=True, force_bn=bn)
         ref = base
         assert y.dtype == torch.float32
         torch.cuda.synchronize()
         assert nerr(y, ref) < TOL_F32
     elif mode == "rowscale":
         rs = torch.rand(M, device=cuda)
-        y = ops.gemm(a, weights.pack_linear(w), N, bias=b, row_scale=rs)
+        y = ops.gemm(a, weights.pack_linear(w), N, bias=b, row_scale=rs, force_bn=bn)
         ref = base * rs[:, None]
     elif mode == "rowbias":
         rb = rnd((M,), cuda, 5)
-        y = ops.gemm(a, weights.pack_linear(w), N, bias=rb, bias_per_row=True)
+        y = ops.gemm(a, weights.pack_linear(w), N, bias=rb, bias_per_row=True, force_bn=bn)
         ref = a.float() @ wb.t() + rb[:, None]
     elif mode == "stepbias":
         tab = rnd((5, N), cuda, 6)
         step = torch.tensor([3, 0], dtype=torch.int32, device=cuda)
-        y = ops.gemm(a, weights.pack_linear(w), N, bias=tab, bias_step_stride=N, step_ptr=step)
+        y = ops.gemm(a, weights.pack_linear(w), N, bias=tab, bias_step_stride=N, step_ptr=step, force_bn=bn)
         ref = a.float() @ wb.t() + tab[3]
     else:  # strided A (a column slice of a wider buffer) and strided weight rows
         big = rnd((M, 3 * K), cuda, 7).bfloat16()
         a2 = big[:, K:2 * K]
         wbig = weights.pack_linear(rnd((N, 2 * K), cuda, 8, K ** -0.5))
-        y = ops.gemm(a2, wbig[:, :K], N, bias=b)
+        y = ops.gemm(a2, wbig[:, :K], N, bias=b, force_bn=bn)
         ref = a2.float() @ wbig[:, :K].float().t() + b
     torch.cuda.synchronize()
     assert nerr(y, ref) < TOL_BF16
@@ -107,6 +111,25 @@ def test_conv3x3(cuda, n, h, w, cin, cout):
     ref = conv_ref([x], wt, b)
     torch.cuda.synchronize()
     assert nerr(y, ref) < TOL_BF16
+
+
+def test_conv3x3_residual_rowscale_silu(cuda):
+    """ResnetBlock2D conv2 (+x) and EMASC conv (SiLU, (1-mask) row scale) on ragged tile geometry (24x20, batch 3)."""
+    from ladi_vton_b200 import ops, weights
+    n, h, w, c = 3, 24, 20, 192
+    x = rnd((n, h, w, c), cuda, 1).bfloat16()
+    res = rnd((n, h, w, c), cuda, 2).bfloat16()
+    wt = rnd((c, c, 3, 3), cuda, 3, (9 * c) ** -0.5)
+    b = rnd((c,), cuda, 4)
+    rs = torch.rand(n * h * w, device=cuda)
+    ref = conv_ref([x], wt, b)
+    for direct in (False, True):
+        y = ops.conv2d([x], weights.pack_conv(wt, [c]), c, bias=b, residual=res, direct_epilogue=direct)
+        torch.cuda.synchronize()
+        assert nerr(y, ref + res.float()) < TOL_BF16
+        y = ops.conv2d([x], weights.pack_conv(wt, [c]), c, bias=b, act=ops.ACT_SILU, row_scale=rs, direct_epilogue=direct)
+        torch.cuda.synchronize()
+        assert nerr(y, F.silu(ref) * rs.view(n, h, w, 1)) < TOL_BF16
 
 
 def test_conv3x3_concat_shortcut(cuda):
@@ -174,7 +197,8 @@ def test_conv_invalid_args_error(cuda):
 # ------------------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("B,heads,nq,nkv", [(2, 5, 768, 768), (1, 2, 128, 128), (2, 3, 192, 192), (3, 2, 48, 48), (2, 5, 768, 77),
                                             (1, 1, 3072, 3072), (2, 2, 200, 333)])
-def test_attention(cuda, B, heads, nq, nkv):
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_attention(cuda, B, heads, nq, nkv, variant):
     from ladi_vton_b200 import ops
     C = heads * 64
     if nq == nkv:  # fused QKV buffer, per-head slices read in place
@@ -184,7 +208,7 @@ def test_attention(cuda, B, heads, nq, nkv):
         q = rnd((B, nq, C), cuda, 1).bfloat16()
         kv = rnd((B, nkv, 2 * C), cuda, 2).bfloat16()
         k, v = kv[..., :C], kv[..., C:]
-    y = ops.attention(q, k, v, heads, 0.125)
+    y = ops.attention(q, k, v, heads, 0.125, variant=variant)
     sp = lambda t: t.float().reshape(B, -1, heads, 64).transpose(1, 2)
     ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(B, nq, C)
     torch.cuda.synchronize()

@@ -76,13 +76,16 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
   }
 }
 
-// ---- GroupNorm pass 2: normalise + affine (+SiLU) (+add), writes the concatenated tensor
+// ---- GroupNorm pass 2: normalise + affine (+SiLU) (+add), writes the concatenated tensor.  Per-channel scale/shift
+// (rstd*gamma, beta - mean*rstd*gamma) are tabulated once per block in shared memory, so the streaming loop is one FMA (+SiLU)
+// per element with no integer division; the (pixel, vector) walk advances incrementally.
 __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x0, int c0, int pitch0, const bf16* __restrict__ x1,
                                                        int c1, int pitch1, int hw, int groups, int chunks, const float* __restrict__ ws,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                        int silu, const bf16* __restrict__ add, int add_pitch, bf16* __restrict__ out,
                                                        int out_pitch, int px_per_block) {
   __shared__ float smean[GN_MAX_GROUPS], srstd[GN_MAX_GROUPS];
+  __shared__ __align__(16) float sa[GN_SLOTS], sb[GN_SLOTS];
   const int n = blockIdx.y, t = threadIdx.x;
   const int C = c0 + c1, nv = C >> 3, cpg = C / groups;
   if (t < groups) {
@@ -96,20 +99,30 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
     srstd[t] = rsqrtf(var + eps);
   }
   __syncthreads();
+  for (int c = t; c < C; c += 256) {
+    const int g = c / cpg;
+    const float a = srstd[g] * __ldg(gamma + c);
+    sa[c] = a;
+    sb[c] = __ldg(beta + c) - smean[g] * a;
+  }
+  __syncthreads();
   const int p0 = blockIdx.x * px_per_block, p1 = min(hw, p0 + px_per_block);
   const int total = (p1 - p0) * nv;
+  const int dv = 256 % nv, dp = 256 / nv;
+  int v = t % nv, px = p0 + t / nv;
   for (int e = t; e < total; e += 256) {
-    const int px = p0 + e / nv, v = e % nv, ch = v * 8;
+    const int ch = v * 8;
     const bf16* src = ch < c0 ? x0 + ((size_t)n * hw + px) * pitch0 + ch : x1 + ((size_t)n * hw + px) * pitch1 + (ch - c0);
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
     float f[8];
     unpack8(u, f);
+    const float4 a0 = *reinterpret_cast<const float4*>(sa + ch), a1 = *reinterpret_cast<const float4*>(sa + ch + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(sb + ch), b1 = *reinterpret_cast<const float4*>(sb + ch + 4);
+    f[0] = fmaf(f[0], a0.x, b0.x); f[1] = fmaf(f[1], a0.y, b0.y); f[2] = fmaf(f[2], a0.z, b0.z); f[3] = fmaf(f[3], a0.w, b0.w);
+    f[4] = fmaf(f[4], a1.x, b1.x); f[5] = fmaf(f[5], a1.y, b1.y); f[6] = fmaf(f[6], a1.z, b1.z); f[7] = fmaf(f[7], a1.w, b1.w);
+    if (silu) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int g = (ch + i) / cpg;
-      float y = (f[i] - smean[g]) * srstd[g] * __ldg(gamma + ch + i) + __ldg(beta + ch + i);
-      if (silu) y = y / (1.f + __expf(-y));
-      f[i] = y;
+      for (int i = 0; i < 8; ++i) f[i] = __fdividef(f[i], 1.f + __expf(-f[i]));
     }
     if (add != nullptr) {
       const uint4 a = __ldg(reinterpret_cast<const uint4*>(add + ((size_t)n * hw + px) * add_pitch + ch));
@@ -119,46 +132,57 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
       for (int i = 0; i < 8; ++i) f[i] += g8[i];
     }
     *reinterpret_cast<uint4*>(out + ((size_t)n * hw + px) * out_pitch + ch) = pack8(f);
+    v += dv; px += dp;
+    if (v >= nv) { v -= nv; ++px; }
   }
 }
 
-// ---- LayerNorm: one warp per row, row cached in registers (C <= 2048)
-__global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, int x_pitch, int rows, int C,
+// ---- LayerNorm: T lanes per row (T = 32/16/8/4), VPL 16-byte vectors per lane, row cached in registers; several rows per warp
+// keep every lane busy for the narrow rows (C = 320: 8 lanes x 5 vectors, 4 rows per warp).
+template <int VPL>
+__global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, int x_pitch, int rows, int C, int T,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                         bf16* __restrict__ out, int out_pitch) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const int nv = C >> 3;
-  float f[8][8];
+  const int rows_per_warp = 32 / T;
+  const int warp = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int sub = lane / T, tl = lane % T;
+  const int row = warp * rows_per_warp + sub;
+  const bool ok = row < rows;
+  float f[VPL][8];
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int v = lane + 32 * j;
-    if (v < nv) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (size_t)row * x_pitch + v * 8));
+  for (int j = 0; j < VPL; ++j) {
+    if (ok) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + (size_t)row * x_pitch + (tl + T * j) * 8));
       unpack8(u, f[j]);
+    } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s += f[j][i];
+      for (int i = 0; i < 8; ++i) f[j][i] = 0.f;
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += f[j][i];
   }
-  const float mean = warp_sum(s) / (float)C;
+  for (int o = T >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
   float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < 8; ++j)
-    if (lane + 32 * j < nv) {
+  for (int j = 0; j < VPL; ++j)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { const float d = f[j][i] - mean; q += d * d; }
-    }
-  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    for (int i = 0; i < 8; ++i) { const float d = f[j][i] - mean; q += d * d; }
+  for (int o = T >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)C + eps);
+  if (!ok) return;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int v = lane + 32 * j;
-    if (v < nv) {
-      float y[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = (f[j][i] - mean) * rstd * __ldg(gamma + v * 8 + i) + __ldg(beta + v * 8 + i);
-      *reinterpret_cast<uint4*>(out + (size_t)row * out_pitch + v * 8) = pack8(y);
-    }
+  for (int j = 0; j < VPL; ++j) {
+    const int c = (tl + T * j) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+    float y[8];
+    y[0] = (f[j][0] - mean) * rstd * g0.x + b0.x; y[1] = (f[j][1] - mean) * rstd * g0.y + b0.y;
+    y[2] = (f[j][2] - mean) * rstd * g0.z + b0.z; y[3] = (f[j][3] - mean) * rstd * g0.w + b0.w;
+    y[4] = (f[j][4] - mean) * rstd * g1.x + b1.x; y[5] = (f[j][5] - mean) * rstd * g1.y + b1.y;
+    y[6] = (f[j][6] - mean) * rstd * g1.z + b1.z; y[7] = (f[j][7] - mean) * rstd * g1.w + b1.w;
+    *reinterpret_cast<uint4*>(out + (size_t)row * out_pitch + c) = pack8(y);
   }
 }
 
@@ -369,7 +393,10 @@ extern "C" int ladi_groupnorm_apply(const void* x0, int c0, int pitch0, const vo
   LADI_CHECK(out_pitch % 8 == 0 && out_pitch >= c0 + c1, "groupnorm out pitch invalid");
   const int chunks = gn_chunks(hw);
   const int nv = (c0 + c1) / 8;
-  int ppb = (256 * 8) / nv;  // ~8 vectors per thread
+  int ppb = (256 * 16) / nv;  // >= 16 vectors per thread, and few enough blocks that the per-block channel table amortises
+  const int target_blocks = (ladi_num_sms() * 4 + n - 1) / n;
+  const int ppb2 = (hw + target_blocks - 1) / target_blocks;
+  if (ppb2 > ppb) ppb = ppb2;
   if (ppb < 1) ppb = 1;
   const int blocks = (hw + ppb - 1) / ppb;
   gn_apply_kernel<<<dim3(blocks, n), 256, 0, STREAM>>>((const bf16*)x0, c0, pitch0, (const bf16*)x1, c1, pitch1, hw, groups, chunks, ws,
@@ -381,7 +408,20 @@ extern "C" int ladi_groupnorm_apply(const void* x0, int c0, int pitch0, const vo
 extern "C" int ladi_layernorm(const void* x, int x_pitch, int rows, int c, const float* gamma, const float* beta, float eps, void* out,
                               int out_pitch, void* stream) {
   LADI_CHECK(c % 8 == 0 && c <= 2048 && x_pitch % 8 == 0 && out_pitch % 8 == 0, "layernorm: C must be a multiple of 8 and <= 2048");
-  layernorm_kernel<<<(rows + 7) / 8, 256, 0, STREAM>>>((const bf16*)x, x_pitch, rows, c, gamma, beta, eps, (bf16*)out, out_pitch);
+  const int nv = c / 8;
+  int T = 0, vpl = 0;
+  for (int t = 4; t <= 32; t *= 2)  // smallest lane group whose per-lane vector count fits the register cache
+    if (nv % t == 0 && nv / t <= 8) { T = t; vpl = nv / t; break; }
+  LADI_CHECK(T != 0, "layernorm: unsupported width %d (need C/8 = T * v with T in {4,8,16,32}, v <= 8)", c);
+  const int rows_per_block = 8 * (32 / T);
+  const int blocks = (rows + rows_per_block - 1) / rows_per_block;
+#define LN_CASE(V) \
+  case V: layernorm_kernel<V><<<blocks, 256, 0, STREAM>>>((const bf16*)x, x_pitch, rows, c, T, gamma, beta, eps, (bf16*)out, out_pitch); break;
+  switch (vpl) {
+    LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
+    default: LADI_CHECK(false, "layernorm: bad vectors per lane %d", vpl);
+  }
+#undef LN_CASE
   LADI_CUDA(cudaGetLastError());
   return LADI_OK;
 }

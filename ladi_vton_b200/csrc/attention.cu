@@ -208,6 +208,7 @@ attention_single_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tO = tmem_base + (SHORT ? 128 : 256);
+  ptx::pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -252,6 +253,7 @@ attention_single_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   }
 
   __syncwarp();
+  ptx::pdl_trigger();
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -299,6 +301,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // TMEM columns: S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)
+  ptx::pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -371,6 +374,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
 
   __syncwarp();
+  ptx::pdl_trigger();
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -416,14 +420,13 @@ extern "C" int ladi_attention_bf16(const ladi_attn_desc* d, void* stream_) {
   const int variant = d->variant;  // 0 auto, 1 single, 2 pair (tests / tuning)
   if ((variant == 0 && d->nkv <= BKV) || (variant == 1 && d->nkv <= BKV)) {
     dim3 grid((d->nq + BQ - 1) / BQ, d->heads, d->batch);
-    attention_single_kernel<true><<<grid, 256, SMEM_SHORT, stream>>>(tq, tk, tv, p);
+    LADI_CUDA(ladi_launch(attention_single_kernel<true>, grid, dim3(256), SMEM_SHORT, stream, tq, tk, tv, p));
   } else if (variant == 1) {
     dim3 grid((d->nq + BQ - 1) / BQ, d->heads, d->batch);
-    attention_single_kernel<false><<<grid, 256, SMEM_SINGLE, stream>>>(tq, tk, tv, p);
+    LADI_CUDA(ladi_launch(attention_single_kernel<false>, grid, dim3(256), SMEM_SINGLE, stream, tq, tk, tv, p));
   } else {
     dim3 grid((d->nq + 2 * BQ - 1) / (2 * BQ), d->heads, d->batch);
-    attention_pair_kernel<<<grid, 384, SMEM_PAIR, stream>>>(tq, tk, tv, p);
+    LADI_CUDA(ladi_launch(attention_pair_kernel, grid, dim3(384), SMEM_PAIR, stream, tq, tk, tv, p));
   }
-  LADI_CUDA(cudaGetLastError());
   return LADI_OK;
 }

@@ -2,6 +2,7 @@
 #include "common.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 static thread_local char g_err[512] = "";
@@ -77,4 +78,13 @@ int ladi_num_sms() {
       sms = 148;
   }
   return sms;
+}
+
+int ladi_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LADI_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v;
 }

@@ -37,3 +37,20 @@ int ladi_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const ui
                           const uint32_t* box, int swizzle_bytes = 128);
 
 int ladi_num_sms();
+int ladi_pdl_enabled();  // env LADI_PDL=0 disables programmatic dependent launch (A/B timing)
+
+#ifdef __CUDACC__
+#include <utility>
+// Every kernel of the library is launched through this helper (programmatic stream serialization attribute, see ptx.cuh).
+template <typename... KArgs, typename... Args>
+inline cudaError_t ladi_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ladi_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+#endif

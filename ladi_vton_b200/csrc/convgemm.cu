@@ -28,6 +28,7 @@ constexpr int NUM_A_MAPS = 8;
 constexpr int MAX_STAGES = 8;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int SLAB_BYTES = BM * 128;  // staging tile: 128 rows x 64 bf16
+constexpr int RES_BUFS = 3;           // residual slabs in flight (TMA prefetch ring, runs ahead across tile boundaries)
 
 struct Segment {       // one run of K blocks read from one tensor map with one spatial shift
   int16_t map, dx, dy, chunks;
@@ -104,12 +105,12 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
   uint8_t* sA = smem;
   uint8_t* sB = sA + STAGES * A_BYTES;
   uint8_t* sOut = sB + STAGES * B_BYTES;                         // 2 staging tiles (staged epilogue only)
-  uint8_t* sRes = sOut + (p.staged ? 2 * SLAB_BYTES : 0);        // 2 residual tiles (staged + residual only)
-  uint8_t* sEnd = sRes + ((p.staged && p.residual != nullptr) ? 2 * SLAB_BYTES : 0);
+  uint8_t* sRes = sOut + (p.staged ? 2 * SLAB_BYTES : 0);        // residual ring (staged + residual only)
+  uint8_t* sEnd = sRes + ((p.staged && p.residual != nullptr) ? RES_BUFS * SLAB_BYTES : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sEnd);
   const uint32_t full0 = ptx::smem_u32(bars), empty0 = full0 + 8 * MAX_STAGES, tfull0 = empty0 + 8 * MAX_STAGES,
                  tempty0 = tfull0 + 16, rfull0 = tempty0 + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 6);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4 + RES_BUFS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -127,8 +128,8 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull0 + 8 * a, 1);
       ptx::mbar_init(tempty0 + 8 * a, 256);
-      ptx::mbar_init(rfull0 + 8 * a, 1);
     }
+    for (int a = 0; a < RES_BUFS; ++a) ptx::mbar_init(rfull0 + 8 * a, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), TMEM_COLS);
@@ -136,6 +137,7 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();  // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   const int num_tiles = p.tiles_m * p.tiles_n;
 
@@ -204,9 +206,29 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
       constexpr int BNo_full = BN;                       // accumulator columns per tile
       const int acc_per_slab = geglu ? 128 : 64;          // accumulator columns feeding one 64-column output slab
       const int c_eff = geglu ? p.c_out / 2 : p.c_out;    // output channels
-      uint32_t rcount = 0;                                // residual loads issued so far (buffer = rcount & 1)
+      uint32_t rcount = 0;                                // residual slabs consumed so far (ring slot = rcount % RES_BUFS)
       uint32_t scount = 0;                                // slabs processed so far (staging buffer = scount & 1)
       const int sw128 = r & 7, sw64 = (r >> 1) & 3;
+      const int BNo = geglu ? BN / 2 : BN;                // output columns per tile
+      // residual producer cursor (elected thread): runs up to RES_BUFS slabs ahead of the consumers, across tile boundaries
+      int ptile = blockIdx.x, pslab = 0;
+      uint32_t pcount = 0;
+      auto issue_residual = [&]() {
+        if (ptile >= num_tiles) return;
+        const TileCoord pc = tile_coord(p, ptile);
+        const int pvalid = min(BN, p.c_out - pc.nt * BN);
+        const int pnslabs = (pvalid + acc_per_slab - 1) / acc_per_slab;
+        const int w = min(64, BNo - 64 * pslab);
+        const uint32_t slot = pcount % RES_BUFS;
+        const uint32_t rb = rfull0 + 8 * slot;
+        ptx::mbar_expect_tx(rb, BM * w * 2);
+        ptx::tma_load_4d(w == 64 ? &emaps.res64 : &emaps.res32, ptx::smem_u32(sRes + slot * SLAB_BYTES), rb, pc.nt * BNo + 64 * pslab, pc.x0,
+                         pc.y0, pc.n0);
+        ++pcount;
+        if (++pslab == pnslabs) { pslab = 0; ptile += gridDim.x; }
+      };
+      if (has_res && elected)
+        for (int i = 0; i < RES_BUFS; ++i) issue_residual();
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
@@ -215,20 +237,12 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
         const int acc_valid = min(BNo_full, p.c_out - acc0);
         const int nslabs = (acc_valid + acc_per_slab - 1) / acc_per_slab;
         const int out0 = geglu ? acc0 / 2 : acc0;                     // first output column of this tile
-        const int BNo = geglu ? BN / 2 : BN;                          // output columns per tile
         const int n = tc.n0 + rn, y = tc.y0 + ry, x = tc.x0 + rx;
         const bool row_ok = (n < p.n_img) && (y < p.H) && (x < p.W);
         const size_t grow = ((size_t)n * p.H + y) * p.W + x;
         const float rscale = (p.row_scale != nullptr && row_ok) ? p.row_scale[grow] : 1.f;
         const float rbias = (p.bias_per_row && bias != nullptr && row_ok) ? bias[grow] : 0.f;
 
-        if (has_res && elected) {  // residual slab 0 of this tile: issued before waiting for the accumulator
-          const int w0 = min(64, BNo);
-          const uint32_t rb = rfull0 + 8 * (rcount & 1);
-          ptx::mbar_expect_tx(rb, BM * w0 * 2);
-          ptx::tma_load_4d(w0 == 64 ? &emaps.res64 : &emaps.res32, ptx::smem_u32(sRes + (rcount & 1) * SLAB_BYTES), rb, out0, tc.x0, tc.y0,
-                           tc.n0);
-        }
         ptx::mbar_wait(tfull0 + 8 * as, aphase);
         ptx::tc_fence_after();
         const uint32_t t_row = tmem_base + as * ACC_STRIDE + ((uint32_t)(ew * 32) << 16);
@@ -236,17 +250,8 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
         for (int s = 0; s < nslabs; ++s, ++scount) {
           const int wout = min(64, BNo - 64 * s);                    // 64, or 32 for the tail slab of BN=160/32 tiles
           const int ocol = out0 + 64 * s;                            // first output column of the slab (global)
-          const uint32_t rbuf = rcount & 1;
-          if (has_res) {
-            if (elected && s + 1 < nslabs) {                          // prefetch the next residual slab into the other buffer
-              const int w1 = min(64, BNo - 64 * (s + 1));
-              const uint32_t rb = rfull0 + 8 * ((rcount + 1) & 1);
-              ptx::mbar_expect_tx(rb, BM * w1 * 2);
-              ptx::tma_load_4d(w1 == 64 ? &emaps.res64 : &emaps.res32, ptx::smem_u32(sRes + ((rcount + 1) & 1) * SLAB_BYTES), rb,
-                               ocol + 64, tc.x0, tc.y0, tc.n0);
-            }
-            ptx::mbar_wait(rfull0 + 8 * rbuf, (rcount >> 1) & 1);
-          }
+          const uint32_t rbuf = rcount % RES_BUFS;
+          if (has_res) ptx::mbar_wait(rfull0 + 8 * rbuf, (rcount / RES_BUFS) & 1);
           uint8_t* ostage = sOut + (scount & 1) * SLAB_BYTES;
           const uint8_t* rstage = sRes + rbuf * SLAB_BYTES;
           // ---- 64 output columns = 2 (or, GEGLU, 4) accumulator chunks of 32
@@ -320,9 +325,12 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
           ptx::fence_proxy_async_smem();                 // staging writes -> visible to the TMA engine
           if (elected) ptx::tma_store_wait_read0();      // the store that used the OTHER staging tile has drained it
           ptx::named_barrier_sync(1, 256);
-          if (elected && ocol < c_eff) {
-            ptx::tma_store_4d(wout == 64 ? &emaps.out64 : &emaps.out32, ptx::smem_u32(ostage), ocol, tc.x0, tc.y0, tc.n0);
-            ptx::tma_store_commit();
+          if (elected) {
+            if (ocol < c_eff) {
+              ptx::tma_store_4d(wout == 64 ? &emaps.out64 : &emaps.out32, ptx::smem_u32(ostage), ocol, tc.x0, tc.y0, tc.n0);
+              ptx::tma_store_commit();
+            }
+            if (has_res) issue_residual();  // the ring slot every thread just finished reading is free again
           }
         }
       }
@@ -415,6 +423,7 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
   }
 
   __syncwarp();
+  ptx::pdl_trigger();
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -424,7 +433,7 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
 }
 
 constexpr size_t SMEM_LIMIT = 232448;  // 227 KiB per CTA
-constexpr size_t SMEM_TAIL = (2 * MAX_STAGES + 6) * 8 + 16 + 1024;  // barriers + TMEM slot + alignment slack
+constexpr size_t SMEM_TAIL = (2 * MAX_STAGES + 4 + RES_BUFS) * 8 + 16 + 1024;  // barriers + TMEM slot + alignment slack
 
 template <int BN>
 int launch(const AMaps& am, const CUtensorMap& tmB, const EMaps& em, KParams& kp, cudaStream_t stream) {
@@ -433,7 +442,7 @@ int launch(const AMaps& am, const CUtensorMap& tmB, const EMaps& em, KParams& kp
     LADI_CUDA(cudaFuncSetAttribute(convgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
     attr_set = true;
   }
-  const size_t staging = kp.staged ? (size_t)(kp.residual != nullptr ? 4 : 2) * SLAB_BYTES : 0;
+  const size_t staging = kp.staged ? (size_t)(kp.residual != nullptr ? 2 + RES_BUFS : 2) * SLAB_BYTES : 0;
   const size_t per_stage = A_BYTES + (size_t)BN * BK * 2;
   int stages = (int)((SMEM_LIMIT - SMEM_TAIL - staging) / per_stage);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -442,8 +451,7 @@ int launch(const AMaps& am, const CUtensorMap& tmB, const EMaps& em, KParams& kp
   const size_t smem = stages * per_stage + staging + SMEM_TAIL;
   const int tiles = kp.tiles_m * kp.tiles_n;
   const int grid = tiles < ladi_num_sms() ? tiles : ladi_num_sms();
-  convgemm_kernel<BN><<<grid, 384, smem, stream>>>(am, tmB, em, kp);
-  LADI_CUDA(cudaGetLastError());
+  LADI_CUDA(ladi_launch(convgemm_kernel<BN>, dim3(grid), dim3(384), smem, stream, am, tmB, em, kp));
   return LADI_OK;
 }
 

@@ -37,6 +37,7 @@ __host__ __device__ inline int gn_chunks(int hw) {
 constexpr int GN_SLOTS = 2560;  // >= max(channels, 256 threads * 8 channels)
 __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x0, int c0, int pitch0, const bf16* __restrict__ x1,
                                                        int c1, int pitch1, int hw, int groups, int chunks, float* __restrict__ ws) {
+  ptx::pdl_wait();
   __shared__ float ps[GN_SLOTS], pq[GN_SLOTS];  // [pixel lane][channel]
   const int n = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
   const int C = c0 + c1, nv = C >> 3, cpg = C / groups;
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
                                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                        int silu, const bf16* __restrict__ add, int add_pitch, bf16* __restrict__ out,
                                                        int out_pitch, int px_per_block) {
+  ptx::pdl_wait();
   __shared__ float smean[GN_MAX_GROUPS], srstd[GN_MAX_GROUPS];
   __shared__ __align__(16) float sa[GN_SLOTS], sb[GN_SLOTS];
   const int n = blockIdx.y, t = threadIdx.x;
@@ -143,6 +145,7 @@ template <int VPL>
 __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__ x, int x_pitch, int rows, int C, int T,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                         bf16* __restrict__ out, int out_pitch) {
+  ptx::pdl_wait();
   const int rows_per_warp = 32 / T;
   const int warp = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int sub = lane / T, tl = lane % T;
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const bf16* __restrict__
 // ---- row softmax fp32 -> bf16
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, int cols, int s_pitch, float scale,
                                                            bf16* __restrict__ out, int out_pitch) {
+  ptx::pdl_wait();
   __shared__ float red[8];
   const float* row = s + (size_t)blockIdx.x * s_pitch;
   bf16* orow = out + (size_t)blockIdx.x * out_pitch;
@@ -213,6 +217,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 }
 
 __global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o, int64_t nvec) {
+  ptx::pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     float x[8], y[8];
     unpack8(__ldg(a + i), x);
@@ -224,6 +229,7 @@ __global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict_
 }
 
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, int n, int h, int w, int cv, uint4* __restrict__ out) {
+  ptx::pdl_wait();
   const int64_t total = (int64_t)n * (2 * h) * (2 * w) * cv;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int v = (int)(i % cv);
@@ -239,6 +245,7 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, int n, int h, int
 // (f > 1: nearest down-sampling, src index = floor(dst * f); gate: `image * (mask < 0.5)` of prepare_mask_and_masked_image)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int n, int c, int h, int w, int f, float scale,
                                     const float* __restrict__ gate, bf16* __restrict__ out, int out_pitch, int c_off) {
+  ptx::pdl_wait();
   const int64_t hw = (int64_t)h * w;
   const int64_t total = (int64_t)n * hw * c;
   const int64_t W = (int64_t)w * f, HW = (int64_t)h * f * W;
@@ -255,6 +262,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int n, int c, i
 
 __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int is_f32, int n, int c, int hw, int x_pitch, int c_off,
                                     float* __restrict__ out) {
+  ptx::pdl_wait();
   const int64_t total = (int64_t)n * c * hw;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t px = i % hw;
@@ -268,6 +276,7 @@ __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, int is_f32, int 
 
 __global__ void posterior_kernel(const float* __restrict__ mom, int m_pitch, const float* __restrict__ noise, int n, int cz, int hw,
                                  float scale, float* __restrict__ out) {
+  ptx::pdl_wait();
   const int64_t total = (int64_t)n * cz * hw;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t px = i % hw;
@@ -282,6 +291,7 @@ __global__ void posterior_kernel(const float* __restrict__ mom, int m_pitch, con
 }
 
 __global__ void inv_mask_kernel(const float* __restrict__ mask, int n, int H, int W, int f, float* __restrict__ out) {
+  ptx::pdl_wait();
   const int h = H / f, w = W / f;
   const int64_t total = (int64_t)n * h * w;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -295,6 +305,7 @@ __global__ void inv_mask_kernel(const float* __restrict__ mask, int n, int H, in
 
 // F.interpolate(mode="bilinear", align_corners=False), exact /8: src = (dst+0.5)*8-0.5 = 8*dst+3.5 -> taps 8d+3, 8d+4 at 0.5
 __global__ void bilinear8_kernel(const float* __restrict__ x, int nc, int H, int W, float* __restrict__ out) {
+  ptx::pdl_wait();
   const int h = H / 8, w = W / 8;
   const int64_t total = (int64_t)nc * h * w;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -313,6 +324,7 @@ __global__ void bilinear8_kernel(const float* __restrict__ x, int nc, int H, int
 __global__ void ddim_cfg_kernel(const float* __restrict__ eps, int eps_pitch, float* __restrict__ lat, bf16* __restrict__ uin,
                                 int in_pitch, int B, int hw, int cfg, float guidance, const float* __restrict__ coef, int* step_ptr,
                                 int advance) {
+  ptx::pdl_wait();
   const int s = step_ptr ? step_ptr[0] : 0;
   const float inv_sa = coef[4 * s], s1a = coef[4 * s + 1], sap = coef[4 * s + 2], s1ap = coef[4 * s + 3];
   const int64_t total = (int64_t)B * 4 * hw;
@@ -348,6 +360,7 @@ __global__ void ddim_cfg_kernel(const float* __restrict__ eps, int eps_pitch, fl
 }
 
 __global__ void image_out_kernel(const void* __restrict__ x, int is_f32, int64_t npx, int x_pitch, float* __restrict__ out) {
+  ptx::pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npx * 3; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t px = i / 3;
     const int ch = (int)(i % 3);
@@ -381,8 +394,7 @@ extern "C" int ladi_groupnorm_stats(const void* x0, int c0, int pitch0, const vo
                                     float* ws, void* stream) {
   if (int e = gn_check(x0, c0, pitch0, x1, c1, pitch1, groups)) return e;
   const int chunks = gn_chunks(hw);
-  gn_stats_kernel<<<dim3(chunks, n), 256, 0, STREAM>>>((const bf16*)x0, c0, pitch0, (const bf16*)x1, c1, pitch1, hw, groups, chunks, ws);
-  LADI_CUDA(cudaGetLastError());
+  LADI_CUDA(ladi_launch(gn_stats_kernel, dim3(dim3(chunks, n)), dim3(256), 0, STREAM, (const bf16*)x0, c0, pitch0, (const bf16*)x1, c1, pitch1, hw, groups, chunks, ws));
   return LADI_OK;
 }
 
@@ -399,9 +411,8 @@ extern "C" int ladi_groupnorm_apply(const void* x0, int c0, int pitch0, const vo
   if (ppb2 > ppb) ppb = ppb2;
   if (ppb < 1) ppb = 1;
   const int blocks = (hw + ppb - 1) / ppb;
-  gn_apply_kernel<<<dim3(blocks, n), 256, 0, STREAM>>>((const bf16*)x0, c0, pitch0, (const bf16*)x1, c1, pitch1, hw, groups, chunks, ws,
-                                                       gamma, beta, eps, silu, (const bf16*)add, add_pitch, (bf16*)out, out_pitch, ppb);
-  LADI_CUDA(cudaGetLastError());
+  LADI_CUDA(ladi_launch(gn_apply_kernel, dim3(dim3(blocks, n)), dim3(256), 0, STREAM, (const bf16*)x0, c0, pitch0, (const bf16*)x1, c1, pitch1, hw, groups, chunks, ws,
+                                                       gamma, beta, eps, silu, (const bf16*)add, add_pitch, (bf16*)out, out_pitch, ppb));
   return LADI_OK;
 }
 
@@ -416,84 +427,73 @@ extern "C" int ladi_layernorm(const void* x, int x_pitch, int rows, int c, const
   const int rows_per_block = 8 * (32 / T);
   const int blocks = (rows + rows_per_block - 1) / rows_per_block;
 #define LN_CASE(V) \
-  case V: layernorm_kernel<V><<<blocks, 256, 0, STREAM>>>((const bf16*)x, x_pitch, rows, c, T, gamma, beta, eps, (bf16*)out, out_pitch); break;
+  case V: LADI_CUDA(ladi_launch(layernorm_kernel<V>, dim3(blocks), dim3(256), 0, STREAM, (const bf16*)x, x_pitch, rows, c, T, gamma, beta, eps, (bf16*)out, out_pitch)); break;
   switch (vpl) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
     default: LADI_CHECK(false, "layernorm: bad vectors per lane %d", vpl);
   }
 #undef LN_CASE
-  LADI_CUDA(cudaGetLastError());
   return LADI_OK;
 }
 
 extern "C" int ladi_softmax_rows(const float* s, int rows, int cols, int s_pitch, float scale, void* out, int out_pitch, void* stream) {
   LADI_CHECK(rows > 0 && cols > 0, "softmax: empty");
-  softmax_rows_kernel<<<rows, 256, 0, STREAM>>>(s, cols, s_pitch, scale, (bf16*)out, out_pitch);
-  LADI_CUDA(cudaGetLastError());
+  LADI_CUDA(ladi_launch(softmax_rows_kernel, dim3(rows), dim3(256), 0, STREAM, s, cols, s_pitch, scale, (bf16*)out, out_pitch));
   return LADI_OK;
 }
 
 extern "C" int ladi_add_bf16(const void* a, const void* b, void* out, int64_t count, void* stream) {
   LADI_CHECK(count % 8 == 0, "add: count must be a multiple of 8");
-  add_kernel<<<grid_for(count / 8), 256, 0, STREAM>>>((const uint4*)a, (const uint4*)b, (uint4*)out, count / 8);
-  LADI_CUDA(cudaGetLastError());
+  LADI_CUDA(ladi_launch(add_kernel, dim3(grid_for(count / 8)), dim3(256), 0, STREAM, (const uint4*)a, (const uint4*)b, (uint4*)out, count / 8));
   return LADI_OK;
 }
 
 extern "C" int ladi_upsample2x_nhwc(const void* x, int n, int h, int w, int c, void* out, void* stream) {
   LADI_CHECK(c % 8 == 0, "upsample: C must be a multiple of 8");
-  upsample2x_kernel<<<grid_for((int64_t)n * 4 * h * w * (c / 8)), 256, 0, STREAM>>>((const uint4*)x, n, h, w, c / 8, (uint4*)out);
-  LADI_CUDA(cudaGetLastError());
+  LADI_CUDA(ladi_launch(upsample2x_kernel, dim3(grid_for((int64_t)n * 4 * h * w * (c / 8))), dim3(256), 0, STREAM, (const uint4*)x, n, h, w, c / 8, (uint4*)out));
   return LADI_OK;
 }
 
 extern "C" int ladi_nchw_f32_to_nhwc_bf16(const float* x, int n, int c, int h, int w, int f, float scale, const float* gate, void* out,
                                           int out_pitch, int c_off, void* stream) {
   LADI_CHECK(f >= 1, "nchw_to_nhwc: bad sampling factor");
-  nchw_to_nhwc_kernel<<<grid_for((int64_t)n * c * h * w), 256, 0, STREAM>>>(x, n, c, h, w, f, scale, gate, (bf16*)out, out_pitch, c_off);
-  LADI_CUDA(cudaGetLastError());
+  LADI_CUDA(ladi_launch(nchw_to_nhwc_kernel, dim3(grid_for((int64_t)n * c * h * w)), dim3(256), 0, STREAM, x, n, c, h, w, f, scale, gate, (bf16*)out, out_pitch, c_off));
   return LADI_OK;
 }
 
 extern "C" int ladi_nhwc_to_nchw_f32(const void* x, int x_is_fp32, int n, int c, int h, int w, int x_pitch, int c_off, float* out,
                                      void* stream) {
-  nhwc_to_nchw_kernel<<<grid_for((int64_t)n * c * h * w), 256, 0, STREAM>>>(x, x_is_fp32, n, c, h * w, x_pitch, c_off, out);
-  LADI_CUDA(cudaGetLastError());
+  LADI_CUDA(ladi_launch(nhwc_to_nchw_kernel, dim3(grid_for((int64_t)n * c * h * w)), dim3(256), 0, STREAM, x, x_is_fp32, n, c, h * w, x_pitch, c_off, out));
   return LADI_OK;
 }
 
 extern "C" int ladi_posterior_sample(const float* moments, int m_pitch, const float* noise_nchw, int n, int cz, int h, int w, float scale,
                                      float* out_nchw, void* stream) {
-  posterior_kernel<<<grid_for((int64_t)n * cz * h * w), 256, 0, STREAM>>>(moments, m_pitch, noise_nchw, n, cz, h * w, scale, out_nchw);
-  LADI_CUDA(cudaGetLastError());
+  LADI_CUDA(ladi_launch(posterior_kernel, dim3(grid_for((int64_t)n * cz * h * w)), dim3(256), 0, STREAM, moments, m_pitch, noise_nchw, n, cz, h * w, scale, out_nchw));
   return LADI_OK;
 }
 
 extern "C" int ladi_inv_mask_rows(const float* mask, int n, int H, int W, int f, float* out, void* stream) {
   LADI_CHECK(f >= 1 && H % f == 0 && W % f == 0, "inv_mask: factor must divide H and W");
-  inv_mask_kernel<<<grid_for((int64_t)n * (H / f) * (W / f)), 256, 0, STREAM>>>(mask, n, H, W, f, out);
-  LADI_CUDA(cudaGetLastError());
+  LADI_CUDA(ladi_launch(inv_mask_kernel, dim3(grid_for((int64_t)n * (H / f) * (W / f))), dim3(256), 0, STREAM, mask, n, H, W, f, out));
   return LADI_OK;
 }
 
 extern "C" int ladi_bilinear_down8(const float* x, int n, int c, int H, int W, float* out, void* stream) {
   LADI_CHECK(H % 8 == 0 && W % 8 == 0, "bilinear_down8: H, W must be multiples of 8");
-  bilinear8_kernel<<<grid_for((int64_t)n * c * (H / 8) * (W / 8)), 256, 0, STREAM>>>(x, n * c, H, W, out);
-  LADI_CUDA(cudaGetLastError());
+  LADI_CUDA(ladi_launch(bilinear8_kernel, dim3(grid_for((int64_t)n * c * (H / 8) * (W / 8))), dim3(256), 0, STREAM, x, n * c, H, W, out));
   return LADI_OK;
 }
 
 extern "C" int ladi_ddim_cfg_step(const float* eps, int eps_pitch, float* latents, void* unet_in, int in_pitch, int B, int h, int w,
                                   int cfg, float guidance, const float* coef, int* step_ptr, int advance, void* stream) {
   LADI_CHECK(eps && latents && unet_in && coef, "ddim: null operand");
-  ddim_cfg_kernel<<<grid_for((int64_t)B * 4 * h * w), 256, 0, STREAM>>>(eps, eps_pitch, latents, (bf16*)unet_in, in_pitch, B, h * w, cfg,
-                                                                         guidance, coef, step_ptr, advance);
-  LADI_CUDA(cudaGetLastError());
+  LADI_CUDA(ladi_launch(ddim_cfg_kernel, dim3(grid_for((int64_t)B * 4 * h * w)), dim3(256), 0, STREAM, eps, eps_pitch, latents, (bf16*)unet_in, in_pitch, B, h * w, cfg,
+                                                                         guidance, coef, step_ptr, advance));
   return LADI_OK;
 }
 
 extern "C" int ladi_image_out(const void* x, int x_is_fp32, int n, int h, int w, int x_pitch, float* out, void* stream) {
-  image_out_kernel<<<grid_for((int64_t)n * h * w * 3), 256, 0, STREAM>>>(x, x_is_fp32, (int64_t)n * h * w, x_pitch, out);
-  LADI_CUDA(cudaGetLastError());
+  LADI_CUDA(ladi_launch(image_out_kernel, dim3(grid_for((int64_t)n * h * w * 3)), dim3(256), 0, STREAM, x, x_is_fp32, (int64_t)n * h * w, x_pitch, out));
   return LADI_OK;
 }

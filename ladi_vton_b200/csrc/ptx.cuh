@@ -49,6 +49,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #endif
 }
 
+// ----------------------------------------------------------------------------------------------- programmatic dependent launch
+// Kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel's prologue (barrier init, TMEM
+// allocation, tensor-map prefetch) overlaps the tail of its predecessor; pdl_wait() blocks until the predecessor grid has
+// completed and its writes are visible, pdl_trigger() lets the successor start being scheduled.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

@@ -63,8 +63,13 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
       ptx::tmem_ld32(ts + c, v);
       ptx::tmem_wait_ld();
       if (c + 32 <= valid) {
+        float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // independent chains: 4x shorter dependency
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; i += 4) {
+          m0 = fmaxf(m0, __uint_as_float(v[i])); m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+          m2 = fmaxf(m2, __uint_as_float(v[i + 2])); m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i)
@@ -75,7 +80,7 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
     const float alpha = ex2(m - m_new);  // 0 on the first tile (m = -inf)
     // pass 2: p = exp2(s*scale - m_new), packed to bf16
     uint32_t pk[64];
-    float sum = 0.f;
+    float sum = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll
     for (int c = 0; c < BKV; c += 32) {
       uint32_t v[32];
@@ -85,11 +90,14 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
       }
       if (c + 32 <= valid) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
+        for (int i = 0; i < 32; i += 4) {
           const float p0 = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
           const float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_new));
-          sum += p0 + p1;
+          const float p2 = ex2(fmaf(__uint_as_float(v[i + 2]), p.scale_log2, -m_new));
+          const float p3 = ex2(fmaf(__uint_as_float(v[i + 3]), p.scale_log2, -m_new));
+          sum += p0; sum1 += p1; sum2 += p2; sum3 += p3;
           pk[(c + i) >> 1] = ptx::pack_bf16(p0, p1);
+          pk[((c + i) >> 1) + 1] = ptx::pack_bf16(p2, p3);
         }
       } else {
 #pragma unroll
@@ -102,7 +110,7 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
         }
       }
     }
-    l = l * alpha + sum;
+    l = l * alpha + ((sum + sum1) + (sum2 + sum3));
     const bool moved = m_new > m;
     m = m_new;
     // P buffer and O are free once P V of the previous tile has completed

@@ -81,6 +81,8 @@ typedef struct ladi_conv_desc {
   int out_fp32;
   int force_bn;              /* 0 = auto; else N tile in {32,64,128,160,192,256} (tests / tuning) */
   int force_direct_epilogue; /* 1 = direct-store epilogue even where the staged TMA-store epilogue applies (tests) */
+  void* splitk_ws;           /* optional fp32 workspace: enables split-K for few-tile / long-K shapes (NULL = never split) */
+  int64_t splitk_ws_bytes;
 } ladi_conv_desc;
 LADI_API int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream);
 

@@ -38,26 +38,32 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// One query row per thread (128 threads): consumes S tiles from TMEM, produces P tiles in shared memory, keeps O normalised.
-//   S for KV tile j lives at tS + s_stride * (j & s_mask); barriers: s_full (per S buffer), p_full (count 128), o_ready.
+// HALVES threads per query row (HALVES = 1: 128 threads per tile; HALVES = 2: 256 threads, the two halves split the key
+// columns of every S tile, the O columns and the P K-chunks, and agree on the running row maximum through shared memory).
+// Consumes S tiles from TMEM, produces P tiles in shared memory, keeps O normalised.
+//   S for KV tile j lives at tS + s_stride * (j & s_mask); barriers: s_full (per S buffer), p_full (count 128*HALVES), o_ready.
+template <int HALVES>
 __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, uint32_t tS, uint32_t s_stride, uint32_t s_mask, uint32_t tO,
                                              uint8_t* sP, uint32_t s_full0, uint32_t p_full, uint32_t o_ready, int ew, int lane, int q0,
-                                             int h, int b) {
+                                             int h, int b, int half, float* xm, uint32_t bar_id) {
+  constexpr int COLS = BKV / HALVES;        // key columns of each S tile owned by this thread
+  constexpr int OCOLS = HD / HALVES;        // O columns owned by this thread
   const int r = ew * 32 + lane;
   const uint32_t lane_off = (uint32_t)(ew * 32) << 16;
+  const int col0 = half * COLS;
   float m = -INFINITY, l = 0.f;
-  uint8_t* prow0 = sP + r * 128;
+  uint8_t* prow0 = sP + r * 128 + (HALVES == 2 ? half * TILE_BYTES : 0);
   const int sw = r & 7;
   for (int j = 0; j < n_tiles; ++j) {
     const uint32_t sb = j & s_mask;
-    const int valid = min(BKV, p.nkv - j * BKV);
+    const int valid = min(COLS, p.nkv - j * BKV - col0);  // may be <= 0 for the upper half of a ragged last tile
     ptx::mbar_wait(s_full0 + 8 * sb, s_mask ? ((j >> 1) & 1) : (j & 1));
     ptx::tc_fence_after();
-    const uint32_t ts = tS + sb * s_stride + lane_off;
+    const uint32_t ts = tS + sb * s_stride + lane_off + col0;
     // pass 1: row maximum
     float mx = -INFINITY;
 #pragma unroll 1
-    for (int c = 0; c < BKV; c += 32) {
+    for (int c = 0; c < COLS; c += 32) {
       if (c >= valid) break;
       uint32_t v[32];
       ptx::tmem_ld32(ts + c, v);
@@ -76,13 +82,19 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
           if (c + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
       }
     }
+    if (HALVES == 2) {  // both halves of a row must scale P and O with the same maximum
+      float* slot = xm + (j & 1) * 256;
+      slot[half * 128 + r] = mx;
+      ptx::named_barrier_sync(bar_id, 256);
+      mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]);
+    }
     const float m_new = fmaxf(m, mx * p.scale_log2);
     const float alpha = ex2(m - m_new);  // 0 on the first tile (m = -inf)
     // pass 2: p = exp2(s*scale - m_new), packed to bf16
-    uint32_t pk[64];
+    uint32_t pk[COLS / 2];
     float sum = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
 #pragma unroll
-    for (int c = 0; c < BKV; c += 32) {
+    for (int c = 0; c < COLS; c += 32) {
       uint32_t v[32];
       if (c < valid) {
         ptx::tmem_ld32(ts + c, v);
@@ -119,19 +131,19 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
       ptx::tc_fence_after();
     }
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {  // 16-byte pieces: 8 per 64-key chunk, XOR-swizzled by (row & 7)
+    for (int q = 0; q < COLS / 8; ++q) {  // 16-byte pieces: 8 per 64-key chunk, XOR-swizzled by (row & 7)
       uint8_t* dst = prow0 + (q >> 3) * TILE_BYTES + (((q & 7) ^ sw) << 4);
       *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
     }
     if (j > 0 && __any_sync(0xffffffffu, moved)) {
 #pragma unroll
-      for (int c = 0; c < HD; c += 32) {
+      for (int c = 0; c < OCOLS; c += 32) {
         uint32_t v[32];
-        ptx::tmem_ld32(tO + lane_off + c, v);
+        ptx::tmem_ld32(tO + lane_off + half * OCOLS + c, v);
         ptx::tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-        ptx::tmem_st32(tO + lane_off + c, v);
+        ptx::tmem_st32(tO + lane_off + half * OCOLS + c, v);
       }
       ptx::tmem_wait_st();
     }
@@ -140,15 +152,21 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
     ptx::mbar_arrive(p_full);
   }
   // ---- output: O / l
+  if (HALVES == 2) {  // row sum = sum over both column halves (they used identical maxima throughout)
+    float* slot = xm + (n_tiles & 1) * 256;
+    slot[half * 128 + r] = l;
+    ptx::named_barrier_sync(bar_id, 256);
+    l += slot[(half ^ 1) * 128 + r];
+  }
   ptx::mbar_wait(o_ready, (n_tiles - 1) & 1);
   ptx::tc_fence_after();
   const int qi = q0 + r;
   const float inv = 1.f / l;
-  bf16* orow = p.out + (size_t)b * p.out_batch_stride + (size_t)qi * p.out_pitch + h * HD;
+  bf16* orow = p.out + (size_t)b * p.out_batch_stride + (size_t)qi * p.out_pitch + h * HD + half * OCOLS;
 #pragma unroll
-  for (int c = 0; c < HD; c += 32) {
+  for (int c = 0; c < OCOLS; c += 32) {
     uint32_t v[32];
-    ptx::tmem_ld32(tO + lane_off + c, v);
+    ptx::tmem_ld32(tO + lane_off + half * OCOLS + c, v);
     ptx::tmem_wait_ld();
     if (qi < p.nq) {
 #pragma unroll
@@ -257,7 +275,7 @@ attention_single_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
   } else if (warp >= 4) {
     // SHORT has a single KV tile, so only S buffer 0 / parity 0 is ever used and the 2-buffer indexing below stays valid
-    softmax_rows(p, n_tiles, tS, BKV, SHORT ? 0u : 1u, tO, sP, s_full0, p_full, o_ready, warp & 3, lane, qt * BQ, h, b);
+    softmax_rows<1>(p, n_tiles, tS, BKV, SHORT ? 0u : 1u, tO, sP, s_full0, p_full, o_ready, warp & 3, lane, qt * BQ, h, b, 0, nullptr, 0);
   }
 
   __syncwarp();
@@ -271,7 +289,7 @@ attention_single_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 }
 
 // ============================================================================================ two query tiles per CTA
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(640, 1)
 attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -280,7 +298,8 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint8_t* sK = sQ + 2 * TILE_BYTES;        // 2 stages
   uint8_t* sV = sK + 2 * TILE_BYTES;        // 2 stages
   uint8_t* sP = sV + 2 * TILE_BYTES;        // 2 query tiles x 2 K-chunks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * TILE_BYTES);
+  float* xm = reinterpret_cast<float*>(sP + 4 * TILE_BYTES);  // row-max / row-sum exchange: [tile][parity][half][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xm + 2 * 2 * 256);
   const uint32_t b0 = ptx::smem_u32(bars);
   const uint32_t q_full = b0, kv_full0 = b0 + 8, kv_empty0 = b0 + 24, s_full0 = b0 + 40 /* A: +0, B: +8 */, p_full0 = b0 + 56,
                  o_ready0 = b0 + 72;
@@ -298,7 +317,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       ptx::mbar_init(kv_full0 + 8 * s, 1);
       ptx::mbar_init(kv_empty0 + 8 * s, 1);
       ptx::mbar_init(s_full0 + 8 * s, 1);
-      ptx::mbar_init(p_full0 + 8 * s, 128);
+      ptx::mbar_init(p_full0 + 8 * s, 256);
       ptx::mbar_init(o_ready0 + 8 * s, 1);
     }
     ptx::fence_barrier_init();
@@ -375,10 +394,11 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
     }
   } else if (warp >= 4) {
-    const int wg = (warp - 4) >> 2;  // 0 = tile A, 1 = tile B
+    const int wg = (warp - 4) >> 3;         // 0 = tile A (warps 4-11), 1 = tile B (warps 12-19)
+    const int half = ((warp - 4) >> 2) & 1;  // which half of the key columns / O columns this warpgroup owns
     if (wg == 0 || has_b)
-      softmax_rows(p, n_tiles, tmem_base + 128 * wg, 0, 0u, tmem_base + 256 + 64 * wg, sP + wg * 2 * TILE_BYTES, s_full0 + 8 * wg,
-                   p_full0 + 8 * wg, o_ready0 + 8 * wg, warp & 3, lane, (qp * 2 + wg) * BQ, h, b);
+      softmax_rows<2>(p, n_tiles, tmem_base + 128 * wg, 0, 0u, tmem_base + 256 + 64 * wg, sP + wg * 2 * TILE_BYTES, s_full0 + 8 * wg,
+                      p_full0 + 8 * wg, o_ready0 + 8 * wg, warp & 3, lane, (qp * 2 + wg) * BQ, h, b, half, xm + wg * 512, 1 + wg);
   }
 
   __syncwarp();
@@ -393,7 +413,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
 constexpr size_t SMEM_SINGLE = 7 * TILE_BYTES + 10 * 8 + 16 + 1024;
 constexpr size_t SMEM_SHORT = 5 * TILE_BYTES + 10 * 8 + 16 + 1024;
-constexpr size_t SMEM_PAIR = 10 * TILE_BYTES + 12 * 8 + 16 + 1024;
+constexpr size_t SMEM_PAIR = 10 * TILE_BYTES + 4 * 256 * 4 + 12 * 8 + 16 + 1024;
 
 int make_map(CUtensorMap* m, const void* ptr, int cols, int tokens, int batch, int pitch, int64_t batch_stride) {
   const uint64_t dims[3] = {(uint64_t)cols, (uint64_t)tokens, (uint64_t)batch};
@@ -434,7 +454,7 @@ extern "C" int ladi_attention_bf16(const ladi_attn_desc* d, void* stream_) {
     LADI_CUDA(ladi_launch(attention_single_kernel<false>, grid, dim3(256), SMEM_SINGLE, stream, tq, tk, tv, p));
   } else {
     dim3 grid((d->nq + 2 * BQ - 1) / (2 * BQ), d->heads, d->batch);
-    LADI_CUDA(ladi_launch(attention_pair_kernel, grid, dim3(384), SMEM_PAIR, stream, tq, tk, tv, p));
+    LADI_CUDA(ladi_launch(attention_pair_kernel, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
   }
   return LADI_OK;
 }

@@ -42,6 +42,8 @@ struct KParams {
   int c_out;
   int nseg, total_kb;
   int stages;                 // smem pipeline depth (runtime: whatever fits beside the staging tiles)
+  int splits, kb_per_split;   // split-K: work item = (tile, split); split s reduces K blocks [s*kb_per_split, ...) into fp32 partials
+  long long split_stride;     // elements between the partial planes of consecutive splits
   int staged;                 // 1 = smem-staged TMA-store epilogue (bf16 out), 0 = direct stores
   Segment seg[MAX_SEG];
   const float* bias;          // [c_out] fp32 (per column) or [M] (per row) or null
@@ -140,18 +142,23 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
   ptx::pdl_wait();  // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_items = num_tiles * p.splits;
 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------------ TMA producer
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int tile = item / p.splits, split = item - tile * p.splits;
+        const int kb0 = split * p.kb_per_split, kb1 = min(p.total_kb, kb0 + p.kb_per_split);
         const TileCoord tc = tile_coord(p, tile);
         int kb = 0;
-        for (int s = 0; s < p.nseg; ++s) {
+        for (int s = 0; s < p.nseg && kb < kb1; ++s) {
           const Segment sg = p.seg[s];
           const CUtensorMap* am = &amaps.m[sg.map];
-          for (int c = 0; c < sg.chunks; ++c, ++kb) {
+          if (kb + sg.chunks <= kb0) { kb += sg.chunks; continue; }
+          for (int c = 0; c < sg.chunks && kb < kb1; ++c, ++kb) {
+            if (kb < kb0) continue;
             ptx::mbar_wait(empty0 + 8 * stage, phase ^ 1);
             const uint32_t fb = full0 + 8 * stage;
             ptx::mbar_expect_tx(fb, A_BYTES + B_BYTES);
@@ -168,12 +175,14 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
       constexpr uint32_t idesc = ptx::idesc_bf16(BM, BN, 0, 0);
       uint32_t stage = 0, phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+        const int split = item % p.splits;
+        const int nkb = min(p.total_kb, (split + 1) * p.kb_per_split) - split * p.kb_per_split;
         ptx::mbar_wait(tempty0 + 8 * as, aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
-        for (int kb = 0; kb < p.total_kb; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(full0 + 8 * stage, phase);
           ptx::tc_fence_after();
           const uint64_t adesc = ptx::smem_desc_sw128(ptx::smem_u32(sA + stage * A_BYTES));
@@ -338,8 +347,9 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
     } else {
       // ================= direct-store epilogue (fp32 outputs, tiny / unaligned N); the two warpgroups alternate 32-column chunks ==
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+        const int tile = item / p.splits, split = item - tile * p.splits;
         const TileCoord tc = tile_coord(p, tile);
         const int nt = tc.nt;
         const int n = tc.n0 + rn, y = tc.y0 + ry, x = tc.x0 + rx;
@@ -397,7 +407,7 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
             for (int j = 0; j < 32; ++j) f[j] *= rscale;
           }
           if (p.out_fp32) {
-            float* orow = reinterpret_cast<float*>(p.out) + grow * p.out_pitch + col0;
+            float* orow = reinterpret_cast<float*>(p.out) + (size_t)split * p.split_stride + grow * p.out_pitch + col0;
             if (ncols == 32 && (p.out_pitch & 3) == 0) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(orow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
@@ -432,6 +442,36 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
   }
 }
 
+// Split-K second pass: out = act(sum_s partial[s] + bias) + residual, bf16.  Partials are summed in split order -> deterministic.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long split_stride, long long rows,
+                                                            int c_out, const float* __restrict__ bias, int bias_step_stride,
+                                                            const int* __restrict__ step_ptr, int act, const bf16* __restrict__ residual,
+                                                            int residual_pitch, bf16* __restrict__ out, int out_pitch) {
+  ptx::pdl_wait();
+  if (bias != nullptr && step_ptr != nullptr) bias += (size_t)(*step_ptr) * bias_step_stride;
+  const int cv = c_out >> 2;
+  const long long total = rows * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / cv;
+    const int col = (int)(i - row * cv) * 4;
+    float4 acc = *reinterpret_cast<const float4*>(ws + row * c_out + col);
+    for (int s = 1; s < splits; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(ws + s * split_stride + row * c_out + col);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (bias != nullptr) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
+      acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
+    }
+    if (act == 1) { acc.x = silu_f(acc.x); acc.y = silu_f(acc.y); acc.z = silu_f(acc.z); acc.w = silu_f(acc.w); }
+    if (residual != nullptr) {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(residual + row * residual_pitch + col));
+      acc.x += ptx::bf16_lo(u.x); acc.y += ptx::bf16_hi(u.x); acc.z += ptx::bf16_lo(u.y); acc.w += ptx::bf16_hi(u.y);
+    }
+    *reinterpret_cast<uint2*>(out + row * out_pitch + col) = make_uint2(ptx::pack_bf16(acc.x, acc.y), ptx::pack_bf16(acc.z, acc.w));
+  }
+}
+
 constexpr size_t SMEM_LIMIT = 232448;  // 227 KiB per CTA
 constexpr size_t SMEM_TAIL = (2 * MAX_STAGES + 4 + RES_BUFS) * 8 + 16 + 1024;  // barriers + TMEM slot + alignment slack
 
@@ -449,7 +489,7 @@ int launch(const AMaps& am, const CUtensorMap& tmB, const EMaps& em, KParams& kp
   LADI_CHECK(stages >= 2, "not enough shared memory for a 2-stage pipeline");
   kp.stages = stages;
   const size_t smem = stages * per_stage + staging + SMEM_TAIL;
-  const int tiles = kp.tiles_m * kp.tiles_n;
+  const int tiles = kp.tiles_m * kp.tiles_n * kp.splits;
   const int grid = tiles < ladi_num_sms() ? tiles : ladi_num_sms();
   LADI_CUDA(ladi_launch(convgemm_kernel<BN>, dim3(grid), dim3(384), smem, stream, am, tmB, em, kp));
   return LADI_OK;
@@ -584,6 +624,32 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
     }
   }
   if (d->act == 2 && kp.staged && BN % 128 != 0) kp.staged = 0;
+
+  // ---- split-K: few output tiles but a long reduction (the 8x6 / 16x12 UNet levels): spread K over otherwise idle SMs,
+  // fp32 partial planes in the caller's workspace, summed (in split order) by splitk_reduce_kernel
+  kp.splits = 1; kp.kb_per_split = total; kp.split_stride = 0;
+  const long long rows = (long long)d->n * d->h_out * d->w_out;
+  bool split = false;
+  if (d->splitk_ws != nullptr && d->force_bn == 0 && !d->out_fp32 && d->act != 2 && d->row_scale == nullptr && !d->bias_per_row &&
+      d->c_out % 4 == 0 && d->out_pitch % 4 == 0 && (d->residual == nullptr || d->residual_pitch % 4 == 0) && total >= 32) {
+    const int bn_s = d->c_out >= 256 ? 256 : (d->c_out >= 128 ? 128 : 64);
+    const long tiles_s = (long)kp.tiles_m * ((d->c_out + bn_s - 1) / bn_s);
+    if (tiles_s * 2 <= sms) {
+      int S = (int)(sms / tiles_s);
+      if (S > total / 8) S = total / 8;
+      if (S > 16) S = 16;
+      if (S >= 2) {
+        const int per = (total + S - 1) / S;
+        S = (total + per - 1) / per;
+        if (S >= 2 && (long long)S * rows * d->c_out * 4 <= d->splitk_ws_bytes) {
+          split = true; BN = bn_s;
+          kp.splits = S; kp.kb_per_split = per; kp.split_stride = rows * d->c_out;
+          kp.staged = 0; kp.out = d->splitk_ws; kp.out_pitch = d->c_out; kp.out_fp32 = 1;
+          kp.bias = nullptr; kp.step_ptr = nullptr; kp.act = 0; kp.residual = nullptr;
+        }
+      }
+    }
+  }
   kp.tiles_n = (d->c_out + BN - 1) / BN;
 
   CUtensorMap tmB;
@@ -607,13 +673,22 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
   } else {
     em.out64 = em.out32 = em.res64 = em.res32 = tmB;
   }
+  int rc = LADI_OK;
   switch (BN) {
-    case 256: return launch<256>(am, tmB, em, kp, stream);
-    case 192: return launch<192>(am, tmB, em, kp, stream);
-    case 160: return launch<160>(am, tmB, em, kp, stream);
-    case 128: return launch<128>(am, tmB, em, kp, stream);
-    case 64: return launch<64>(am, tmB, em, kp, stream);
-    case 32: return launch<32>(am, tmB, em, kp, stream);
+    case 256: rc = launch<256>(am, tmB, em, kp, stream); break;
+    case 192: rc = launch<192>(am, tmB, em, kp, stream); break;
+    case 160: rc = launch<160>(am, tmB, em, kp, stream); break;
+    case 128: rc = launch<128>(am, tmB, em, kp, stream); break;
+    case 64: rc = launch<64>(am, tmB, em, kp, stream); break;
+    case 32: rc = launch<32>(am, tmB, em, kp, stream); break;
     default: LADI_CHECK(false, "unsupported BN %d", BN);
   }
+  if (rc != LADI_OK || !split) return rc;
+  const long long vecs = rows * (d->c_out / 4);
+  long long blocks = (vecs + 255) / 256;
+  if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
+  LADI_CUDA(ladi_launch(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, (const float*)d->splitk_ws, kp.splits,
+                        kp.split_stride, rows, d->c_out, d->bias, d->bias_step_stride, d->step_ptr, d->act,
+                        reinterpret_cast<const bf16*>(d->residual), d->residual_pitch, reinterpret_cast<bf16*>(d->out), d->out_pitch));
+  return LADI_OK;
 }

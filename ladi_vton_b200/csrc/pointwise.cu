@@ -35,12 +35,17 @@ __host__ __device__ inline int gn_chunks(int hw) {
 // ---- GroupNorm pass 1: per (image, pixel chunk) partial {sum, sum of squares} per group.  Deterministic: per-thread channel
 // partials go to shared memory and are folded in a fixed order (no floating-point atomics), so two runs are bit-identical.
 constexpr int GN_SLOTS = 2560;  // >= max(channels, 256 threads * 8 channels)
+// grid = (pixel chunks, images, group splits): blockIdx.z owns groups [z*gps, (z+1)*gps) i.e. a contiguous channel range, so the
+// low-resolution levels (48..192 pixels, 1280..2560 channels) still spread over the whole GPU.
 __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ x0, int c0, int pitch0, const bf16* __restrict__ x1,
                                                        int c1, int pitch1, int hw, int groups, int chunks, float* __restrict__ ws) {
   ptx::pdl_wait();
-  __shared__ float ps[GN_SLOTS], pq[GN_SLOTS];  // [pixel lane][channel]
+  __shared__ float ps[GN_SLOTS], pq[GN_SLOTS];  // [pixel lane][channel of this block's range]
   const int n = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
-  const int C = c0 + c1, nv = C >> 3, cpg = C / groups;
+  const int Ctot = c0 + c1, cpg = Ctot / groups;
+  const int gps = groups / gridDim.z;            // groups per block
+  const int cbeg = blockIdx.z * gps * cpg;       // first channel of this block (multiple of 8 by construction)
+  const int C = gps * cpg, nv = C >> 3;
   const int per = (hw + chunks - 1) / chunks;
   const int p0 = chunk * per, p1 = min(hw, p0 + per);
   const int lanes_v = nv < 256 ? nv : 256;
@@ -48,7 +53,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
   if (t < lanes_v * k) {
     const int tv = t % lanes_v, tp = t / lanes_v;
     for (int v = tv; v < nv; v += lanes_v) {
-      const int ch = v * 8;
+      const int ch = cbeg + v * 8;
       const bf16* base;
       int pitch;
       if (ch < c0) { base = x0 + (size_t)n * hw * pitch0 + ch; pitch = pitch0; }
@@ -64,15 +69,15 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
         for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { ps[tp * C + ch + i] = s[i]; pq[tp * C + ch + i] = q[i]; }
+      for (int i = 0; i < 8; ++i) { ps[tp * C + v * 8 + i] = s[i]; pq[tp * C + v * 8 + i] = q[i]; }
     }
   }
   __syncthreads();
-  if (t < groups) {
+  if (t < gps) {
     float s = 0.f, q = 0.f;
     for (int l = 0; l < k; ++l)
       for (int c = t * cpg; c < (t + 1) * cpg; ++c) { s += ps[l * C + c]; q += pq[l * C + c]; }
-    float* dst = ws + (((size_t)n * chunks + chunk) * groups + t) * 2;
+    float* dst = ws + (((size_t)n * chunks + chunk) * groups + blockIdx.z * gps + t) * 2;
     dst[0] = s; dst[1] = q;
   }
 }
@@ -394,7 +399,12 @@ extern "C" int ladi_groupnorm_stats(const void* x0, int c0, int pitch0, const vo
                                     float* ws, void* stream) {
   if (int e = gn_check(x0, c0, pitch0, x1, c1, pitch1, groups)) return e;
   const int chunks = gn_chunks(hw);
-  LADI_CUDA(ladi_launch(gn_stats_kernel, dim3(dim3(chunks, n)), dim3(256), 0, STREAM, (const bf16*)x0, c0, pitch0, (const bf16*)x1, c1, pitch1, hw, groups, chunks, ws));
+  // split the groups over blockIdx.z until the grid covers the GPU twice; each split must own whole groups and whole 16-byte vectors
+  int gsplit = 1;
+  while (gsplit < 16 && (long)chunks * n * gsplit < 2L * ladi_num_sms() && groups % (gsplit * 2) == 0 &&
+         ((c0 + c1) / (gsplit * 2)) % 8 == 0 && (c0 % ((c0 + c1) / (gsplit * 2)) == 0 || c1 == 0 || true))
+    gsplit *= 2;
+  LADI_CUDA(ladi_launch(gn_stats_kernel, dim3(dim3(chunks, n, gsplit)), dim3(256), 0, STREAM, (const bf16*)x0, c0, pitch0, (const bf16*)x1, c1, pitch1, hw, groups, chunks, ws));
   return LADI_OK;
 }
 

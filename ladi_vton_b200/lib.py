@@ -21,7 +21,7 @@ class ConvDesc(C.Structure):
         ("bias", C.c_void_p), ("bias_per_row", C.c_int), ("bias_step_stride", C.c_int), ("step_ptr", C.c_void_p),
         ("residual", C.c_void_p), ("residual_pitch", C.c_int),
         ("row_scale", C.c_void_p), ("act", C.c_int),
-        ("out", C.c_void_p), ("out_pitch", C.c_int), ("out_fp32", C.c_int), ("force_bn", C.c_int), ("force_direct_epilogue", C.c_int),
+        ("out", C.c_void_p), ("out_pitch", C.c_int), ("out_fp32", C.c_int), ("force_bn", C.c_int), ("force_direct_epilogue", C.c_int), ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64),
     ]
 
 

@@ -45,13 +45,25 @@ def _nhwc(t):
     return n, h, w, c, pitch
 
 
+_SPLITK_WS = {}
+SPLITK_WS_BYTES = 64 << 20
+
+
+def splitk_workspace(device):
+    """Persistent fp32 scratch for split-K partial sums (one per device; allocated before any graph capture)."""
+    ws = _SPLITK_WS.get(device)
+    if ws is None:
+        ws = _SPLITK_WS[device] = torch.empty(SPLITK_WS_BYTES // 4, dtype=torch.float32, device=device)
+    return ws
+
+
 def padded_k(channels):
     return (channels + BK - 1) // BK * BK
 
 
 def conv2d(srcs, weight, c_out, *, ksize=3, stride=1, pad_lo=1, shortcut=(), bias=None, bias_per_row=False,
            bias_step_stride=0, step_ptr=None, residual=None, row_scale=None, act=ACT_NONE, out=None, out_fp32=False,
-           force_bn=0, direct_epilogue=False):
+           force_bn=0, direct_epilogue=False, split_k=True):
     """Implicit-GEMM convolution over the channel-concat of `srcs` (+ fused 1x1 over `shortcut` tensors).
     `weight`: packed bf16 [c_out, k_total] (see weights.pack_conv).  Returns the NHWC output tensor."""
     assert 1 <= len(srcs) <= 2 and len(shortcut) <= 2
@@ -96,6 +108,9 @@ def conv2d(srcs, weight, c_out, *, ksize=3, stride=1, pad_lo=1, shortcut=(), bia
         d.row_scale = row_scale.data_ptr()
     d.act, d.out, d.out_pitch, d.out_fp32, d.force_bn = act, out.data_ptr(), op, int(out_fp32), force_bn
     d.force_direct_epilogue = int(direct_epilogue)
+    if split_k:
+        ws = splitk_workspace(srcs[0].device)
+        d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), ws.numel() * 4
     # algorithmic flops: 2 * output pixels * c_out * true reduction length (padding channels excluded)
     k_true = ksize * ksize * sum(int(t.shape[3]) for t in srcs) + sum(int(t.shape[3]) for t in shortcut)
     _call("ladi_conv2d_bf16", 2.0 * n * h_out * w_out * c_out * k_true, C.byref(d), _stream(),

@@ -132,6 +132,39 @@ def test_conv3x3_residual_rowscale_silu(cuda):
         assert nerr(y, F.silu(ref) * rs.view(n, h, w, 1)) < TOL_BF16
 
 
+@pytest.mark.parametrize("mode", ["plain", "residual", "silu", "stepbias"])
+def test_conv3x3_split_k(cuda, mode):
+    """8x6 UNet level (768 output rows, K = 11520): few tiles, long reduction -> split-K partial planes + deterministic reduce."""
+    from ladi_vton_b200 import ops, weights
+    n, h, w, c = 16, 8, 6, 1280
+    x = rnd((n, h, w, c), cuda, 1).bfloat16()
+    wt = rnd((c, c, 3, 3), cuda, 2, (9 * c) ** -0.5)
+    b = rnd((c,), cuda, 3)
+    ref = conv_ref([x], wt, b)
+    kw = {}
+    if mode == "residual":
+        res = rnd((n, h, w, c), cuda, 4).bfloat16()
+        kw["residual"] = res
+        ref = ref + res.float()
+    elif mode == "silu":
+        kw["act"] = ops.ACT_SILU
+        ref = F.silu(ref)
+    packed = weights.pack_conv(wt, [c])
+    if mode == "stepbias":
+        tab = rnd((3, c), cuda, 5)
+        step = torch.tensor([2, 0], dtype=torch.int32, device=cuda)
+        y = ops.conv2d([x], packed, c, bias=tab, bias_step_stride=c, step_ptr=step)
+        y0 = ops.conv2d([x], packed, c, bias=tab, bias_step_stride=c, step_ptr=step, split_k=False)
+        ref = conv_ref([x], wt, tab[2])
+    else:
+        y = ops.conv2d([x], packed, c, bias=b, **kw)
+        y0 = ops.conv2d([x], packed, c, bias=b, split_k=False, **kw)
+    torch.cuda.synchronize()
+    assert nerr(y, ref) < TOL_BF16 and nerr(y0, ref) < TOL_BF16
+    assert torch.equal(y, ops.conv2d([x], packed, c, bias=(tab if mode == "stepbias" else b),
+                                     **({"bias_step_stride": c, "step_ptr": step} if mode == "stepbias" else kw)))  # deterministic
+
+
 def test_conv3x3_concat_shortcut(cuda):
     """UNet up-block resnet conv2: 3x3 over h + fused 1x1 conv_shortcut over the (virtual) concat [x, skip]."""
     from ladi_vton_b200 import ops, weights

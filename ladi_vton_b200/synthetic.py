@@ -47,7 +47,11 @@ def random_state_dict(shapes, seed, device="cpu", fast=False):
             bound = 1.0 / math.sqrt(fan.get(base, shp[0]))
         if fast:  # timing-only weights (CPU baseline legs): tile one random block instead of drawing ~1e9 values
             n = math.prod(shp)
-            sd[k] = (block.repeat((n + block.numel() - 1) // block.numel())[:n] * bound).reshape(shp)
+            t = torch.empty(n, device=device)
+            for o in range(0, n, block.numel()):  # in-place tiling: one pass over fresh memory, no temporaries
+                m = min(block.numel(), n - o)
+                torch.mul(block[:m], bound, out=t[o:o + m])
+            sd[k] = t.view(shp)
         else:
             sd[k] = torch.empty(shp, device=device).uniform_(-bound, bound, generator=g)
     return sd

@@ -42,7 +42,7 @@ __device__ __forceinline__ float ex2(float x) {
 // columns of every S tile, the O columns and the P K-chunks, and agree on the running row maximum through shared memory).
 // Consumes S tiles from TMEM, produces P tiles in shared memory, keeps O normalised.
 //   S for KV tile j lives at tS + s_stride * (j & s_mask); barriers: s_full (per S buffer), p_full (count 128*HALVES), o_ready.
-template <int HALVES>
+template <int HALVES, bool SINGLE_READ>
 __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, uint32_t tS, uint32_t s_stride, uint32_t s_mask, uint32_t tO,
                                              uint8_t* sP, uint32_t s_full0, uint32_t p_full, uint32_t o_ready, int ew, int lane, int q0,
                                              int h, int b, int half, float* xm, uint32_t bar_id) {
@@ -60,6 +60,62 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
     ptx::mbar_wait(s_full0 + 8 * sb, s_mask ? ((j >> 1) & 1) : (j & 1));
     ptx::tc_fence_after();
     const uint32_t ts = tS + sb * s_stride + lane_off + col0;
+    bool moved;
+    float alpha;
+    if constexpr (SINGLE_READ) {
+    // ---- one TMEM read per tile: this thread's COLS scores stay in registers for both the maximum and the exponentials
+    uint32_t v[COLS];
+#pragma unroll
+    for (int c = 0; c < COLS; c += 32) {
+      if (c < valid) ptx::tmem_ld32(ts + c, reinterpret_cast<uint32_t(&)[32]>(v[c]));
+    }
+    ptx::tmem_wait_ld();
+    float mx = -INFINITY;
+    if (valid >= COLS) {
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;  // independent chains
+#pragma unroll
+      for (int i = 0; i < COLS; i += 4) {
+        m0 = fmaxf(m0, __uint_as_float(v[i])); m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+        m2 = fmaxf(m2, __uint_as_float(v[i + 2])); m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+      }
+      mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    } else {
+#pragma unroll
+      for (int i = 0; i < COLS; ++i)
+        if (i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+    }
+    if (HALVES == 2) {  // both halves of a row must scale P and O with the same maximum
+      float* slot = xm + (j & 1) * 256;
+      slot[half * 128 + r] = mx;
+      ptx::named_barrier_sync(bar_id, 256);
+      mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]);
+    }
+    const float m_new = fmaxf(m, mx * p.scale_log2);
+    alpha = ex2(m - m_new);  // 0 on the first tile (m = -inf)
+    moved = m_new > m;
+    m = m_new;
+    // P buffer and O are free once P V of the previous tile has completed
+    if (j > 0) {
+      ptx::mbar_wait(o_ready, (j - 1) & 1);
+      ptx::tc_fence_after();
+    }
+    // ---- p = exp2(s*scale - m_new) -> bf16, streamed to the swizzled P tile 8 keys (16 bytes) at a time
+    float sum = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+#pragma unroll
+    for (int q = 0; q < COLS / 8; ++q) {
+      float e[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x = ex2(fmaf(__uint_as_float(v[8 * q + i]), p.scale_log2, -m_new));
+        e[i] = (valid >= COLS || 8 * q + i < valid) ? x : 0.f;
+      }
+      sum += e[0] + e[4]; sum1 += e[1] + e[5]; sum2 += e[2] + e[6]; sum3 += e[3] + e[7];
+      uint8_t* dst = prow0 + (q >> 3) * TILE_BYTES + (((q & 7) ^ sw) << 4);
+      *reinterpret_cast<uint4*>(dst) =
+          make_uint4(ptx::pack_bf16(e[0], e[1]), ptx::pack_bf16(e[2], e[3]), ptx::pack_bf16(e[4], e[5]), ptx::pack_bf16(e[6], e[7]));
+    }
+    l = l * alpha + ((sum + sum1) + (sum2 + sum3));
+    } else {
     // pass 1: row maximum
     float mx = -INFINITY;
 #pragma unroll 1
@@ -89,7 +145,7 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
       mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]);
     }
     const float m_new = fmaxf(m, mx * p.scale_log2);
-    const float alpha = ex2(m - m_new);  // 0 on the first tile (m = -inf)
+    alpha = ex2(m - m_new);  // 0 on the first tile (m = -inf)
     // pass 2: p = exp2(s*scale - m_new), packed to bf16
     uint32_t pk[COLS / 2];
     float sum = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
@@ -123,7 +179,7 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
       }
     }
     l = l * alpha + ((sum + sum1) + (sum2 + sum3));
-    const bool moved = m_new > m;
+    moved = m_new > m;
     m = m_new;
     // P buffer and O are free once P V of the previous tile has completed
     if (j > 0) {
@@ -134,6 +190,7 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
     for (int q = 0; q < COLS / 8; ++q) {  // 16-byte pieces: 8 per 64-key chunk, XOR-swizzled by (row & 7)
       uint8_t* dst = prow0 + (q >> 3) * TILE_BYTES + (((q & 7) ^ sw) << 4);
       *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
     }
     if (j > 0 && __any_sync(0xffffffffu, moved)) {
 #pragma unroll
@@ -275,7 +332,7 @@ attention_single_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
   } else if (warp >= 4) {
     // SHORT has a single KV tile, so only S buffer 0 / parity 0 is ever used and the 2-buffer indexing below stays valid
-    softmax_rows<1>(p, n_tiles, tS, BKV, SHORT ? 0u : 1u, tO, sP, s_full0, p_full, o_ready, warp & 3, lane, qt * BQ, h, b, 0, nullptr, 0);
+    softmax_rows<1, !SHORT>(p, n_tiles, tS, BKV, SHORT ? 0u : 1u, tO, sP, s_full0, p_full, o_ready, warp & 3, lane, qt * BQ, h, b, 0, nullptr, 0);
   }
 
   __syncwarp();
@@ -289,6 +346,7 @@ attention_single_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 }
 
 // ============================================================================================ two query tiles per CTA
+template <bool SR>
 __global__ void __launch_bounds__(640, 1)
 attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
@@ -397,7 +455,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int wg = (warp - 4) >> 3;         // 0 = tile A (warps 4-11), 1 = tile B (warps 12-19)
     const int half = ((warp - 4) >> 2) & 1;  // which half of the key columns / O columns this warpgroup owns
     if (wg == 0 || has_b)
-      softmax_rows<2>(p, n_tiles, tmem_base + 128 * wg, 0, 0u, tmem_base + 256 + 64 * wg, sP + wg * 2 * TILE_BYTES, s_full0 + 8 * wg,
+      softmax_rows<2, SR>(p, n_tiles, tmem_base + 128 * wg, 0, 0u, tmem_base + 256 + 64 * wg, sP + wg * 2 * TILE_BYTES, s_full0 + 8 * wg,
                       p_full0 + 8 * wg, o_ready0 + 8 * wg, warp & 3, lane, (qp * 2 + wg) * BQ, h, b, half, xm + wg * 512, 1 + wg);
   }
 
@@ -442,10 +500,11 @@ extern "C" int ladi_attention_bf16(const ladi_attn_desc* d, void* stream_) {
   if (!attr_set) {
     LADI_CUDA(cudaFuncSetAttribute(attention_single_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE));
     LADI_CUDA(cudaFuncSetAttribute(attention_single_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SHORT));
-    LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
+    LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
+    LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
     attr_set = true;
   }
-  const int variant = d->variant;  // 0 auto, 1 single, 2 pair (tests / tuning)
+  const int variant = d->variant;  // 0 auto, 1 single, 2 pair (two TMEM passes), 3 pair (single TMEM read) (tests / tuning)
   if ((variant == 0 && d->nkv <= BKV) || (variant == 1 && d->nkv <= BKV)) {
     dim3 grid((d->nq + BQ - 1) / BQ, d->heads, d->batch);
     LADI_CUDA(ladi_launch(attention_single_kernel<true>, grid, dim3(256), SMEM_SHORT, stream, tq, tk, tv, p));
@@ -454,7 +513,8 @@ extern "C" int ladi_attention_bf16(const ladi_attn_desc* d, void* stream_) {
     LADI_CUDA(ladi_launch(attention_single_kernel<false>, grid, dim3(256), SMEM_SINGLE, stream, tq, tk, tv, p));
   } else {
     dim3 grid((d->nq + 2 * BQ - 1) / (2 * BQ), d->heads, d->batch);
-    LADI_CUDA(ladi_launch(attention_pair_kernel, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
+    if (variant == 3) LADI_CUDA(ladi_launch(attention_pair_kernel<true>, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
+    else LADI_CUDA(ladi_launch(attention_pair_kernel<false>, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
   }
   return LADI_OK;
 }

@@ -83,8 +83,9 @@ for B, heads, nq, nkv in [(16, 5, 3072, 3072), (16, 10, 768, 768), (16, 20, 192,
     C = heads * 64
     q = rnd(B, nq, C); k = rnd(B, nkv, C); v = rnd(B, nkv, C)
     out = torch.empty_like(q)
-    t = timeit(lambda: ops.attention(q, k, v, heads, 0.125, out=out))
-    print(f"  attn B={B} heads={heads} nq={nq} nkv={nkv}: {t:7.1f} us  {4 * B * heads * nq * nkv * 64 / t / 1e6:7.1f} TFLOP/s")
+    for var in ((0, 1, 2, 3) if nkv > 128 else (0,)):
+        t = timeit(lambda: ops.attention(q, k, v, heads, 0.125, out=out, variant=var))
+        print(f"  attn B={B} heads={heads} nq={nq} nkv={nkv} variant={var}: {t:7.1f} us  {4 * B * heads * nq * nkv * 64 / t / 1e6:7.1f} TFLOP/s")
 
 print("== empty-ish launch floor")
 a = rnd(8, 64); wt = weights.pack_linear(torch.randn(8, 64, device=dev)); out = torch.empty((8, 8), dtype=torch.bfloat16, device=dev)

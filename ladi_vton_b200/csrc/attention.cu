@@ -90,7 +90,8 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
       ptx::named_barrier_sync(bar_id, 256);
       mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]);
     }
-    const float m_new = fmaxf(m, mx * p.scale_log2);
+    const float m_true = mx * p.scale_log2;
+    const float m_new = (m_true > m + 8.f) ? m_true : m;  // lazy rescaling, see the two-pass path
     alpha = ex2(m - m_new);  // 0 on the first tile (m = -inf)
     moved = m_new > m;
     m = m_new;
@@ -144,8 +145,11 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
       ptx::named_barrier_sync(bar_id, 256);
       mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]);
     }
-    const float m_new = fmaxf(m, mx * p.scale_log2);
-    alpha = ex2(m - m_new);  // 0 on the first tile (m = -inf)
+    // lazy rescaling: the reference maximum m only moves when the true row maximum exceeds it by more than 2^8; until then P is
+    // scaled with the stale m (values <= 256, exact in bf16/fp32 range) and O / l need no correction -- O/l is invariant to m
+    const float m_true = mx * p.scale_log2;
+    const float m_new = (m_true > m + 8.f) ? m_true : m;
+    alpha = ex2(m - m_new);  // 0 on the first tile (m = -inf), 1 when the reference did not move
     // pass 2: p = exp2(s*scale - m_new), packed to bf16
     uint32_t pk[COLS / 2];
     float sum = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;

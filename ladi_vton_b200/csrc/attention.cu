@@ -350,22 +350,26 @@ attention_single_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 }
 
 // ============================================================================================ two query tiles per CTA
+// Tile B runs ONE KV tile behind tile A: while warpgroup A is in its softmax the tensor core executes B's PV / QK^T and vice
+// versa, so MMA latency is hidden instead of being added to every iteration.  K/V ring of 3 stages (tile t is needed from
+// S_A(t), issued in iteration t-1, until PV_B(t), issued in iteration t+1).
+constexpr int PAIR_KV_STAGES = 3;
 template <bool SR>
 __global__ void __launch_bounds__(640, 1)
 attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                       // 2 query tiles
-  uint8_t* sK = sQ + 2 * TILE_BYTES;        // 2 stages
-  uint8_t* sV = sK + 2 * TILE_BYTES;        // 2 stages
-  uint8_t* sP = sV + 2 * TILE_BYTES;        // 2 query tiles x 2 K-chunks
+  uint8_t* sQ = smem;                                   // 2 query tiles
+  uint8_t* sK = sQ + 2 * TILE_BYTES;                    // 3 stages
+  uint8_t* sV = sK + PAIR_KV_STAGES * TILE_BYTES;       // 3 stages
+  uint8_t* sP = sV + PAIR_KV_STAGES * TILE_BYTES;       // 2 query tiles x 2 K-chunks
   float* xm = reinterpret_cast<float*>(sP + 4 * TILE_BYTES);  // row-max / row-sum exchange: [tile][parity][half][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(xm + 2 * 2 * 256);
   const uint32_t b0 = ptx::smem_u32(bars);
-  const uint32_t q_full = b0, kv_full0 = b0 + 8, kv_empty0 = b0 + 24, s_full0 = b0 + 40 /* A: +0, B: +8 */, p_full0 = b0 + 56,
-                 o_ready0 = b0 + 72;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  const uint32_t q_full = b0, kv_full0 = b0 + 8, kv_empty0 = b0 + 32, s_full0 = b0 + 56 /* A: +0, B: +8 */, p_full0 = b0 + 72,
+                 o_ready0 = b0 + 88;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qp = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -375,9 +379,11 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
     ptx::mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < PAIR_KV_STAGES; ++s) {
       ptx::mbar_init(kv_full0 + 8 * s, 1);
       ptx::mbar_init(kv_empty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(s_full0 + 8 * s, 1);
       ptx::mbar_init(p_full0 + 8 * s, 256);
       ptx::mbar_init(o_ready0 + 8 * s, 1);
@@ -398,8 +404,8 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       ptx::tma_load_3d(&tmQ, ptx::smem_u32(sQ), q_full, h * HD, qp * 2 * BQ, b);
       if (has_b) ptx::tma_load_3d(&tmQ, ptx::smem_u32(sQ + TILE_BYTES), q_full, h * HD, (qp * 2 + 1) * BQ, b);
       for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        ptx::mbar_wait(kv_empty0 + 8 * st, ((j >> 1) & 1) ^ 1);
+        const int st = j % PAIR_KV_STAGES;
+        ptx::mbar_wait(kv_empty0 + 8 * st, ((j / PAIR_KV_STAGES) & 1) ^ 1);
         const uint32_t fb = kv_full0 + 8 * st;
         ptx::mbar_expect_tx(fb, 2 * TILE_BYTES);
         ptx::tma_load_3d(&tmK, ptx::smem_u32(sK + st * TILE_BYTES), fb, h * HD, j * BKV, b);
@@ -413,44 +419,39 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const uint64_t pB0 = ptx::smem_desc_sw128(ptx::smem_u32(sP + 2 * TILE_BYTES)),
                      pB1 = ptx::smem_desc_sw128(ptx::smem_u32(sP + 3 * TILE_BYTES));
       const uint32_t tSA = tmem_base, tSB = tmem_base + 128, tOA = tmem_base + 256, tOB = tmem_base + 320;
+      auto kdesc = [&](int t) { return ptx::smem_desc_sw128(ptx::smem_u32(sK + (t % PAIR_KV_STAGES) * TILE_BYTES)); };
+      auto vdesc = [&](int t) { return ptx::smem_desc_sw128(ptx::smem_u32(sV + (t % PAIR_KV_STAGES) * TILE_BYTES)); };
       ptx::mbar_wait(q_full, 0);
       ptx::mbar_wait(kv_full0, 0);
       ptx::tc_fence_after();
-      {
-        const uint64_t kd = ptx::smem_desc_sw128(ptx::smem_u32(sK));
-        issue_qk(tSA, qdA, kd);
-        ptx::mma_commit(s_full0);
-        if (has_b) {
-          issue_qk(tSB, qdB, kd);
-          ptx::mma_commit(s_full0 + 8);
-        }
-      }
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1, nst = st ^ 1;
-        const bool more = j + 1 < n_tiles;
-        const uint64_t vd = ptx::smem_desc_sw128(ptx::smem_u32(sV + st * TILE_BYTES));
-        const uint64_t kd_next = ptx::smem_desc_sw128(ptx::smem_u32(sK + nst * TILE_BYTES));
-        // ---- tile A: O_A += P_A(j) V(j); then S_A(j+1) so warpgroup A can start its next softmax at once
-        ptx::mbar_wait(p_full0, j & 1);
-        ptx::tc_fence_after();
-        issue_pv(tOA, pA0, pA1, vd, j == 0);
-        ptx::mma_commit(o_ready0);
-        if (more) {
-          ptx::mbar_wait(kv_full0 + 8 * nst, ((j + 1) >> 1) & 1);
+      issue_qk(tSA, qdA, kdesc(0));
+      ptx::mma_commit(s_full0);
+      for (int j = 0; j <= n_tiles; ++j) {
+        if (j < n_tiles) {
+          // ---- tile A, KV tile j: O_A += P_A(j) V(j); then S_A(j+1) so warpgroup A can start its next softmax at once
+          ptx::mbar_wait(p_full0, j & 1);
           ptx::tc_fence_after();
-          issue_qk(tSA, qdA, kd_next);
-          ptx::mma_commit(s_full0);
+          issue_pv(tOA, pA0, pA1, vdesc(j), j == 0);
+          ptx::mma_commit(o_ready0);
+          if (j + 1 < n_tiles) {
+            ptx::mbar_wait(kv_full0 + 8 * ((j + 1) % PAIR_KV_STAGES), ((j + 1) / PAIR_KV_STAGES) & 1);
+            ptx::tc_fence_after();
+            issue_qk(tSA, qdA, kdesc(j + 1));
+            ptx::mma_commit(s_full0);
+          }
         }
-        // ---- tile B
-        if (has_b) {
-          ptx::mbar_wait(p_full0 + 8, j & 1);
-          ptx::tc_fence_after();
-          issue_pv(tOB, pB0, pB1, vd, j == 0);
-          ptx::mma_commit(o_ready0 + 8);
+        // ---- tile B, one KV tile behind
+        if (j > 0) {
+          if (has_b) {
+            ptx::mbar_wait(p_full0 + 8, (j - 1) & 1);
+            ptx::tc_fence_after();
+            issue_pv(tOB, pB0, pB1, vdesc(j - 1), j == 1);
+            ptx::mma_commit(o_ready0 + 8);
+          }
+          ptx::mma_commit(kv_empty0 + 8 * ((j - 1) % PAIR_KV_STAGES));  // both query tiles are done with KV tile j-1
         }
-        ptx::mma_commit(kv_empty0 + 8 * st);  // K/V stage j reusable once everything issued so far has completed
-        if (has_b && more) {
-          issue_qk(tSB, qdB, kd_next);
+        if (has_b && j < n_tiles) {
+          issue_qk(tSB, qdB, kdesc(j));  // kv_full(j) was already observed for tile A
           ptx::mma_commit(s_full0 + 8);
         }
       }
@@ -475,7 +476,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
 constexpr size_t SMEM_SINGLE = 7 * TILE_BYTES + 10 * 8 + 16 + 1024;
 constexpr size_t SMEM_SHORT = 5 * TILE_BYTES + 10 * 8 + 16 + 1024;
-constexpr size_t SMEM_PAIR = 10 * TILE_BYTES + 4 * 256 * 4 + 12 * 8 + 16 + 1024;
+constexpr size_t SMEM_PAIR = (2 + 2 * PAIR_KV_STAGES + 4) * TILE_BYTES + 4 * 256 * 4 + 14 * 8 + 16 + 1024;
 
 int make_map(CUtensorMap* m, const void* ptr, int cols, int tokens, int batch, int pitch, int64_t batch_stride) {
   const uint64_t dims[3] = {(uint64_t)cols, (uint64_t)tokens, (uint64_t)batch};

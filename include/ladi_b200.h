@@ -35,6 +35,7 @@ extern "C" {
 #define LADI_ACT_NONE 0
 #define LADI_ACT_SILU 1
 #define LADI_ACT_GEGLU 2
+#define LADI_ACT_GELU 3 /* GELU(erf): CLIP encoder-layer MLP and the adapter's projection MLP (inversion_adapter.py:12-20) */
 
 LADI_API const char* ladi_last_error(void);
 LADI_API int ladi_abi_version(void);
@@ -118,6 +119,12 @@ LADI_API int ladi_layernorm(const void* x, int x_pitch, int rows, int c, const f
                    int out_pitch, void* stream);
 /* Row softmax fp32 -> bf16 (VAE mid-block AttentionBlock: softmax in fp32, Appendix A.5). */
 LADI_API int ladi_softmax_rows(const float* s, int rows, int cols, int s_pitch, float scale, void* out, int out_pitch, void* stream);
+
+/* CLS-row attention of the inversion adapter's CLIP ViT-H encoder layer (16 heads, head_dim 80, 257 tokens): only token 0 of the
+ * layer output is consumed (/root/reference/src/models/inversion_adapter.py:22-28), so only the CLS query is attended.
+ * q0 [batch, heads*head_dim] bf16, kv [batch, tokens, >= 2*heads*head_dim] bf16 (K columns then V columns) -> out [batch, heads*head_dim]. */
+LADI_API int ladi_cls_attention(const void* q0, int q_pitch, const void* kv, int kv_pitch, int batch, int tokens, int heads, int head_dim,
+                       float scale, void* out, int out_pitch, void* stream);
 
 /* ---- pointwise glue ------------------------------------------------------------------------------------------------- */
 /* out = a + b (bf16, equal pitch-free dense [count]); VAE decoder `sample += int_feat` (vae.py:193). */

@@ -5,6 +5,7 @@ Public surface mirrors the reference (miccunifi/ladi-vton): `StableDiffusionTryO
 (diffusers 0.14, built in hubconf.py / src/inference.py).  All arithmetic runs in libladi_b200.so (include/ladi_b200.h);
 there is no CPU or library fallback.
 """
+from .adapter import InversionAdapter  # noqa: F401
 from .pipeline import StableDiffusionPipelineOutput, StableDiffusionTryOnePipeline  # noqa: F401
 from .scheduler import DDIMScheduler  # noqa: F401
 from .unet import UNet2DConditionModel, unet_param_shapes  # noqa: F401

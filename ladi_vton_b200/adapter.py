@@ -1,0 +1,101 @@
+"""B200-native InversionAdapter -- drop-in for /root/reference/src/models/inversion_adapter.py:5-28 built with the dims of
+hubconf.py:16-27 (CLIP ViT-H vision hidden 1280, 16 heads of 80, MLP 5120; projection 1280 -> 5120 -> 5120 -> 16384) and called at
+src/inference.py:276-277.  State-dict keys: encoder_layers.0.{self_attn.{q,k,v,out}_proj, layer_norm1, mlp.fc1, mlp.fc2, layer_norm2},
+post_layernorm, layers.{0,3,6}.
+
+Only the CLS row of the encoder layer's output is consumed (inversion_adapter.py:26), so after LayerNorm-1 and the K/V projection of
+all 257 tokens, everything (query, attention, out-proj, MLP, projection head) runs on one row per image: 136 M weights are read once
+per call -- an HBM-bound chain of GEMMs on the tcgen05 kernel with GELU(erf) / residual epilogues.
+"""
+import torch
+
+from . import ops
+from .weights import f32, pack_linear
+
+
+class InversionAdapter:
+    def __init__(self, input_dim=1280, hidden_dim=5120, output_dim=16384, config=None, num_encoder_layers=1, dropout=0.5, heads=16, mlp_dim=5120):
+        if config is not None:  # accept the reference's `config=config.vision_config`
+            heads = getattr(config, "num_attention_heads", heads)
+            mlp_dim = getattr(config, "intermediate_size", mlp_dim)
+        if num_encoder_layers != 1:
+            raise NotImplementedError("the reference hub constructor uses exactly one encoder layer (hubconf.py:22)")
+        self.dim, self.hidden, self.out_dim, self.heads, self.mlp_dim = input_dim, hidden_dim, output_dim, heads, mlp_dim
+        self.device = torch.device("cpu")
+        self._sd, self.P = None, None
+
+    def eval(self):
+        return self
+
+    def requires_grad_(self, flag=False):
+        return self
+
+    def param_shapes(self):
+        d, S = self.dim, {}
+        e = "encoder_layers.0."
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            S[e + f"self_attn.{n}.weight"], S[e + f"self_attn.{n}.bias"] = (d, d), (d,)
+        for n in ("layer_norm1", "layer_norm2"):
+            S[e + n + ".weight"], S[e + n + ".bias"] = (d,), (d,)
+        S[e + "mlp.fc1.weight"], S[e + "mlp.fc1.bias"] = (self.mlp_dim, d), (self.mlp_dim,)
+        S[e + "mlp.fc2.weight"], S[e + "mlp.fc2.bias"] = (d, self.mlp_dim), (d,)
+        S["post_layernorm.weight"], S["post_layernorm.bias"] = (d,), (d,)
+        S["layers.0.weight"], S["layers.0.bias"] = (self.hidden, d), (self.hidden,)
+        S["layers.3.weight"], S["layers.3.bias"] = (self.hidden, self.hidden), (self.hidden,)
+        S["layers.6.weight"], S["layers.6.bias"] = (self.out_dim, self.hidden), (self.out_dim,)
+        return S
+
+    def load_state_dict(self, sd, strict=True):
+        want = self.param_shapes()
+        bad = [k for k in want if k not in sd or tuple(sd[k].shape) != tuple(want[k])] + [k for k in sd if k not in want]
+        if strict and bad:
+            raise RuntimeError(f"InversionAdapter state_dict mismatch: {bad[:6]}")
+        self._sd = {k: v.detach() for k, v in sd.items()}
+        if self.device.type == "cuda":
+            self._pack()
+        return self
+
+    def to(self, device=None, dtype=None, **kw):
+        if isinstance(device, torch.dtype):
+            device = None
+        if device is not None:
+            device = torch.device(device)
+            if device.type != "cuda":
+                raise RuntimeError("ladi_vton_b200 InversionAdapter runs on CUDA (sm_100a) only; there is no CPU path")
+            self.device = device
+            if self._sd is not None:
+                self._pack()
+        return self
+
+    def _pack(self):
+        g = lambda k: self._sd[k].to(self.device, torch.float32)
+        e = "encoder_layers.0."
+        P = {}
+        P["ln1"] = (f32(g(e + "layer_norm1.weight")), f32(g(e + "layer_norm1.bias")))
+        P["ln2"] = (f32(g(e + "layer_norm2.weight")), f32(g(e + "layer_norm2.bias")))
+        P["lnp"] = (f32(g("post_layernorm.weight")), f32(g("post_layernorm.bias")))
+        P["kv.w"] = pack_linear(torch.cat([g(e + "self_attn.k_proj.weight"), g(e + "self_attn.v_proj.weight")]))
+        P["kv.b"] = f32(torch.cat([g(e + "self_attn.k_proj.bias"), g(e + "self_attn.v_proj.bias")]))
+        for n, k in (("q", e + "self_attn.q_proj"), ("o", e + "self_attn.out_proj"), ("fc1", e + "mlp.fc1"), ("fc2", e + "mlp.fc2"),
+                     ("l0", "layers.0"), ("l3", "layers.3"), ("l6", "layers.6")):
+            P[n + ".w"], P[n + ".b"] = pack_linear(g(k + ".weight")), f32(g(k + ".bias"))
+        self.P = P
+
+    def __call__(self, x):
+        """x [B, 257, 1280] (CLIP vision last_hidden_state, any float dtype) -> [B, 16384] bf16."""
+        P, d = self.P, self.dim
+        B, T, _ = x.shape
+        hd = d // self.heads
+        xb = x.to(self.device, torch.bfloat16).contiguous()
+        y = ops.layernorm(xb.view(B * T, d), *P["ln1"])                                  # pre-LN over all tokens
+        kv = ops.gemm(y, P["kv.w"], 2 * d, bias=P["kv.b"]).view(B, T, 2 * d)
+        y0 = y.view(B, T, d)[:, 0]                                                      # CLS rows, pitch T*d
+        q0 = ops.gemm(y0, P["q.w"], d, bias=P["q.b"])
+        a = ops.cls_attention(q0, kv, self.heads, hd, hd ** -0.5)
+        x0 = ops.gemm(a, P["o.w"], d, bias=P["o.b"], residual=xb[:, 0])                 # x + attn
+        h = ops.gemm(ops.layernorm(x0, *P["ln2"]), P["fc1.w"], self.mlp_dim, bias=P["fc1.b"], act=ops.ACT_GELU)
+        x0 = ops.gemm(h, P["fc2.w"], d, bias=P["fc2.b"], residual=x0)                   # x + mlp
+        z = ops.layernorm(x0, *P["lnp"])
+        z = ops.gemm(z, P["l0.w"], self.hidden, bias=P["l0.b"], act=ops.ACT_GELU)        # Dropout inactive in eval
+        z = ops.gemm(z, P["l3.w"], self.hidden, bias=P["l3.b"], act=ops.ACT_GELU)
+        return ops.gemm(z, P["l6.w"], self.out_dim, bias=P["l6.b"])

@@ -221,6 +221,56 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   for (int c = t; c < cols; c += 256) orow[c] = __float2bfloat16(__expf((row[c] - mx) * scale) * inv);
 }
 
+// ---- CLS-row attention of the inversion adapter's CLIP encoder layer: only token 0 of the layer output is consumed
+// (/root/reference/src/models/inversion_adapter.py:26), so the query is the CLS row alone; one block per (head, image).
+//   q0 [B, heads*hd] (bias included, unscaled), kv [B, T, 2*heads*hd] (K then V), out [B, heads*hd]
+__global__ void __launch_bounds__(128) cls_attention_kernel(const bf16* __restrict__ q0, int q_pitch, const bf16* __restrict__ kv,
+                                                            int kv_pitch, int T, int heads, int hd, float scale, bf16* __restrict__ out,
+                                                            int out_pitch) {
+  ptx::pdl_wait();
+  extern __shared__ float sm[];  // [hd] query, [T] probabilities
+  float* sq = sm;
+  float* sp = sm + hd;
+  __shared__ float red[4];
+  const int h = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+  const int C = heads * hd;
+  for (int d = t; d < hd; d += 128) sq[d] = __bfloat162float(q0[(size_t)b * q_pitch + h * hd + d]) * scale;
+  __syncthreads();
+  const bf16* kb = kv + (size_t)b * T * kv_pitch + h * hd;
+  float mx = -INFINITY;
+  for (int tok = t; tok < T; tok += 128) {
+    const bf16* kr = kb + (size_t)tok * kv_pitch;
+    float s = 0.f;
+    for (int d = 0; d < hd; d += 2) {
+      const __nv_bfloat162 k2 = *reinterpret_cast<const __nv_bfloat162*>(kr + d);
+      s += sq[d] * __low2float(k2) + sq[d + 1] * __high2float(k2);
+    }
+    sp[tok] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  if ((t & 31) == 0) red[t >> 5] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int tok = t; tok < T; tok += 128) {
+    const float e = __expf(sp[tok] - mx);
+    sp[tok] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  if ((t & 31) == 0) red[t >> 5] = sum;
+  __syncthreads();
+  const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
+  const bf16* vb = kb + C;
+  for (int d = t; d < hd; d += 128) {
+    float acc = 0.f;
+    for (int tok = 0; tok < T; ++tok) acc += sp[tok] * __bfloat162float(vb[(size_t)tok * kv_pitch + d]);
+    out[(size_t)b * out_pitch + h * hd + d] = __float2bfloat16(acc * inv);
+  }
+}
+
 __global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o, int64_t nvec) {
   ptx::pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
@@ -449,6 +499,17 @@ extern "C" int ladi_layernorm(const void* x, int x_pitch, int rows, int c, const
 extern "C" int ladi_softmax_rows(const float* s, int rows, int cols, int s_pitch, float scale, void* out, int out_pitch, void* stream) {
   LADI_CHECK(rows > 0 && cols > 0, "softmax: empty");
   LADI_CUDA(ladi_launch(softmax_rows_kernel, dim3(rows), dim3(256), 0, STREAM, s, cols, s_pitch, scale, (bf16*)out, out_pitch));
+  return LADI_OK;
+}
+
+extern "C" int ladi_cls_attention(const void* q0, int q_pitch, const void* kv, int kv_pitch, int batch, int tokens, int heads, int head_dim,
+                                  float scale, void* out, int out_pitch, void* stream) {
+  LADI_CHECK(q0 && kv && out && batch > 0 && tokens > 0 && heads > 0 && head_dim > 0 && head_dim % 2 == 0, "cls_attention: bad arguments");
+  LADI_CHECK(kv_pitch % 2 == 0 && (heads * head_dim) % 2 == 0, "cls_attention: pitches must be even");
+  const size_t smem = (size_t)(head_dim + tokens) * sizeof(float);
+  LADI_CHECK(smem <= 48 * 1024, "cls_attention: too many tokens");
+  LADI_CUDA(ladi_launch(cls_attention_kernel, dim3(heads, batch), dim3(128), smem, STREAM, (const bf16*)q0, q_pitch, (const bf16*)kv, kv_pitch, tokens,
+                        heads, head_dim, scale, (bf16*)out, out_pitch));
   return LADI_OK;
 }
 

@@ -47,6 +47,7 @@ SIGNATURES = {
     "ladi_groupnorm_apply": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _F, _I, _P, _I, _P, _I, _P], _I),
     "ladi_layernorm": ([_P, _I, _I, _I, _P, _P, _F, _P, _I, _P], _I),
     "ladi_softmax_rows": ([_P, _I, _I, _I, _F, _P, _I, _P], _I),
+    "ladi_cls_attention": ([_P, _I, _P, _I, _I, _I, _I, _I, _F, _P, _I, _P], _I),
     "ladi_add_bf16": ([_P, _P, _P, _L, _P], _I),
     "ladi_upsample2x_nhwc": ([_P, _I, _I, _I, _I, _P, _P], _I),
     "ladi_nchw_f32_to_nhwc_bf16": ([_P, _I, _I, _I, _I, _I, _F, _P, _P, _I, _I, _P], _I),

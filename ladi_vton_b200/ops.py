@@ -11,7 +11,7 @@ import torch
 from . import lib
 from .lib import AttnDesc, ConvDesc
 
-ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_GELU = 0, 1, 2, 3
 BK = 64
 PROFILE = None  # bench.py: set to a list to bracket every launch with CUDA events -> (name, start, end, algorithmic flops)
 
@@ -199,6 +199,15 @@ def softmax_rows(s, scale, out=None):
     if out is None:
         out = torch.empty(s.shape, dtype=torch.bfloat16, device=s.device)
     lib.call("ladi_softmax_rows", _ptr(s), s.shape[0], s.shape[1], s.stride(0), scale, _ptr(out), out.stride(0), _stream())
+    return out
+
+
+def cls_attention(q0, kv, heads, head_dim, scale):
+    """q0 [B, heads*hd] bf16 (CLS query), kv [B, T, 2*heads*hd] bf16 (K | V) -> [B, heads*hd] bf16."""
+    B, T = kv.shape[0], kv.shape[1]
+    assert q0.dtype == torch.bfloat16 and kv.dtype == torch.bfloat16 and kv.stride(2) == 1 and q0.stride(1) == 1
+    out = torch.empty((B, heads * head_dim), dtype=torch.bfloat16, device=q0.device)
+    lib.call("ladi_cls_attention", _ptr(q0), q0.stride(0), _ptr(kv), kv.stride(1), B, T, heads, head_dim, scale, _ptr(out), out.stride(0), _stream())
     return out
 
 

@@ -138,3 +138,20 @@ def test_unet_full_forward(cuda):
     err = rel_l2(y, ref)
     print("full UNet forward rel-L2 vs fp32 oracle:", err)
     assert err < 2e-2
+
+
+def test_inversion_adapter_full(cuda):
+    """hubconf.py:16-27 dims (136,360,704 parameters): CLIP ViT-H features [B,257,1280] -> 16 pseudo-word tokens [B,16384]."""
+    from ladi_vton_b200 import InversionAdapter, synthetic as S
+    from ladi_oracle.parts import InversionAdapter as OA
+    eng = InversionAdapter()
+    sd = S.random_state_dict(eng.param_shapes(), 4321)
+    oa = OA().eval(); oa.load_state_dict(sd)
+    x = torch.randn((3, 257, 1280), generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        ref = oa(x)
+    y = eng.load_state_dict(sd).to(cuda)(x)
+    assert y.shape == ref.shape == (3, 16384)
+    err = rel_l2(y, ref)
+    print("inversion adapter rel-L2 vs fp32 oracle:", err)
+    assert err < 2e-2

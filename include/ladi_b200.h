@@ -99,6 +99,7 @@ typedef struct ladi_attn_desc {
   void* out; int out_pitch; int64_t out_batch_stride;
   float scale;               /* softmax(scale * q k^T) */
   int variant;               /* 0 = auto; 1 = one query tile per CTA; 2 = two query tiles per CTA (tests / tuning) */
+  void* trace;               /* optional device int64[8192]: per-phase clock64() stamps of CTA (0,0,0) (tools/attn_trace.py); NULL */
 } ladi_attn_desc;
 LADI_API int ladi_attention_bf16(const ladi_attn_desc* d, void* stream);
 

@@ -30,7 +30,14 @@ struct AttnParams {
   int out_pitch;
   int64_t out_batch_stride;
   float scale_log2;  // scale * log2(e)
+  long long* trace;  // optional per-phase clock64() trace of CTA (0,0,0) (tools/attn_trace.py); null in production
 };
+
+#define TRACE(slot)                                                                         \
+  do {                                                                                      \
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && trace_ok) \
+      p.trace[trace_base + (slot)] = clock64();                                             \
+  } while (0)
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -51,14 +58,19 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
   const int r = ew * 32 + lane;
   const uint32_t lane_off = (uint32_t)(ew * 32) << 16;
   const int col0 = half * COLS;
+  const bool trace_ok = (ew == 0 && lane == 0);
+  int trace_base = 0;
   float m = -INFINITY, l = 0.f;
   uint8_t* prow0 = sP + r * 128 + (HALVES == 2 ? half * TILE_BYTES : 0);
   const int sw = r & 7;
   for (int j = 0; j < n_tiles; ++j) {
     const uint32_t sb = j & s_mask;
     const int valid = min(COLS, p.nkv - j * BKV - col0);  // may be <= 0 for the upper half of a ragged last tile
+    trace_base = 1024 * (int)(bar_id * 2 + half) + 8 * j;  // bar_id: 1 = tile A, 2 = tile B
+    TRACE(0);
     ptx::mbar_wait(s_full0 + 8 * sb, s_mask ? ((j >> 1) & 1) : (j & 1));
     ptx::tc_fence_after();
+    TRACE(1);
     const uint32_t ts = tS + sb * s_stride + lane_off + col0;
     bool moved;
     float alpha;
@@ -139,12 +151,14 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
           if (c + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
       }
     }
+    TRACE(2);
     if (HALVES == 2) {  // both halves of a row must scale P and O with the same maximum
       float* slot = xm + (j & 1) * 256;
       slot[half * 128 + r] = mx;
       ptx::named_barrier_sync(bar_id, 256);
       mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]);
     }
+    TRACE(3);
     // lazy rescaling: the reference maximum m only moves when the true row maximum exceeds it by more than 2^8; until then P is
     // scaled with the stale m (values <= 256, exact in bf16/fp32 range) and O / l need no correction -- O/l is invariant to m
     const float m_true = mx * p.scale_log2;
@@ -185,11 +199,13 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
     l = l * alpha + ((sum + sum1) + (sum2 + sum3));
     moved = m_new > m;
     m = m_new;
+    TRACE(4);
     // P buffer and O are free once P V of the previous tile has completed
     if (j > 0) {
       ptx::mbar_wait(o_ready, (j - 1) & 1);
       ptx::tc_fence_after();
     }
+    TRACE(5);
 #pragma unroll
     for (int q = 0; q < COLS / 8; ++q) {  // 16-byte pieces: 8 per 64-key chunk, XOR-swizzled by (row & 7)
       uint8_t* dst = prow0 + (q >> 3) * TILE_BYTES + (((q & 7) ^ sw) << 4);
@@ -208,9 +224,11 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
       }
       ptx::tmem_wait_st();
     }
+    TRACE(6);
     ptx::tc_fence_before();
     ptx::fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor core (async proxy)
     ptx::mbar_arrive(p_full);
+    TRACE(7);
   }
   // ---- output: O / l
   if (HALVES == 2) {  // row sum = sum over both column halves (they used identical maxima throughout)
@@ -298,40 +316,51 @@ attention_single_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   ptx::pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_expect_tx(q_full, TILE_BYTES);
       ptx::tma_load_3d(&tmQ, ptx::smem_u32(sQ), q_full, h * HD, qt * BQ, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = SHORT ? 0 : (j & 1);
-        ptx::mbar_wait(kv_empty0 + 8 * st, ((j >> 1) & 1) ^ 1);
-        const uint32_t fb = kv_full0 + 8 * st;
+    }
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = SHORT ? 0 : (j & 1);
+      ptx::mbar_wait(kv_empty0 + 8 * st, ((j >> 1) & 1) ^ 1);
+      const uint32_t fb = kv_full0 + 8 * st;
+      if (ptx::elect_one()) {
         ptx::mbar_expect_tx(fb, 2 * TILE_BYTES);
         ptx::tma_load_3d(&tmK, ptx::smem_u32(sK + st * TILE_BYTES), fb, h * HD, j * BKV, b);
         ptx::tma_load_3d(&tmV, ptx::smem_u32(sV + st * TILE_BYTES), fb, h * HD, j * BKV, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint64_t qdesc = ptx::smem_desc_sw128(ptx::smem_u32(sQ));
-      const uint64_t pdesc0 = ptx::smem_desc_sw128(ptx::smem_u32(sP));
-      const uint64_t pdesc1 = ptx::smem_desc_sw128(ptx::smem_u32(sP + TILE_BYTES));
-      ptx::mbar_wait(q_full, 0);
-      for (int j = 0; j <= n_tiles; ++j) {
-        if (j < n_tiles) {
-          const int st = SHORT ? 0 : (j & 1);
-          ptx::mbar_wait(kv_full0 + 8 * st, (j >> 1) & 1);
-          ptx::tc_fence_after();
-          issue_qk(tS + st * BKV, qdesc, ptx::smem_desc_sw128(ptx::smem_u32(sK + st * TILE_BYTES)));
+    // MMA issuer: warp-uniform loop, one elected lane issues (see ptx::elect_one)
+    const uint64_t qdesc = ptx::smem_desc_sw128(ptx::smem_u32(sQ));
+    const uint64_t pdesc0 = ptx::smem_desc_sw128(ptx::smem_u32(sP));
+    const uint64_t pdesc1 = ptx::smem_desc_sw128(ptx::smem_u32(sP + TILE_BYTES));
+    ptx::mbar_wait(q_full, 0);
+    for (int j = 0; j <= n_tiles; ++j) {
+      if (j < n_tiles) {
+        const int st = SHORT ? 0 : (j & 1);
+        ptx::mbar_wait(kv_full0 + 8 * st, (j >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint64_t kd = ptx::smem_desc_sw128(ptx::smem_u32(sK + st * TILE_BYTES));
+        if (ptx::elect_one()) {
+          issue_qk(tS + st * BKV, qdesc, kd);
           ptx::mma_commit(s_full0 + 8 * st);
         }
-        if (j > 0) {
-          const int i = j - 1, st = SHORT ? 0 : (i & 1);
-          ptx::mbar_wait(p_full, i & 1);
-          ptx::tc_fence_after();
-          issue_pv(tO, pdesc0, pdesc1, ptx::smem_desc_sw128(ptx::smem_u32(sV + st * TILE_BYTES)), i == 0);
+        __syncwarp();
+      }
+      if (j > 0) {
+        const int i = j - 1, st = SHORT ? 0 : (i & 1);
+        ptx::mbar_wait(p_full, i & 1);
+        ptx::tc_fence_after();
+        const uint64_t vd = ptx::smem_desc_sw128(ptx::smem_u32(sV + st * TILE_BYTES));
+        if (ptx::elect_one()) {
+          issue_pv(tO, pdesc0, pdesc1, vd, i == 0);
           ptx::mma_commit(kv_empty0 + 8 * st);
           ptx::mma_commit(o_ready);
         }
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -399,61 +428,84 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   ptx::pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_expect_tx(q_full, (has_b ? 2 : 1) * TILE_BYTES);
       ptx::tma_load_3d(&tmQ, ptx::smem_u32(sQ), q_full, h * HD, qp * 2 * BQ, b);
       if (has_b) ptx::tma_load_3d(&tmQ, ptx::smem_u32(sQ + TILE_BYTES), q_full, h * HD, (qp * 2 + 1) * BQ, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % PAIR_KV_STAGES;
-        ptx::mbar_wait(kv_empty0 + 8 * st, ((j / PAIR_KV_STAGES) & 1) ^ 1);
-        const uint32_t fb = kv_full0 + 8 * st;
+    }
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j % PAIR_KV_STAGES;
+      ptx::mbar_wait(kv_empty0 + 8 * st, ((j / PAIR_KV_STAGES) & 1) ^ 1);
+      const uint32_t fb = kv_full0 + 8 * st;
+      if (ptx::elect_one()) {
         ptx::mbar_expect_tx(fb, 2 * TILE_BYTES);
         ptx::tma_load_3d(&tmK, ptx::smem_u32(sK + st * TILE_BYTES), fb, h * HD, j * BKV, b);
         ptx::tma_load_3d(&tmV, ptx::smem_u32(sV + st * TILE_BYTES), fb, h * HD, j * BKV, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint64_t qdA = ptx::smem_desc_sw128(ptx::smem_u32(sQ)), qdB = ptx::smem_desc_sw128(ptx::smem_u32(sQ + TILE_BYTES));
-      const uint64_t pA0 = ptx::smem_desc_sw128(ptx::smem_u32(sP)), pA1 = ptx::smem_desc_sw128(ptx::smem_u32(sP + TILE_BYTES));
-      const uint64_t pB0 = ptx::smem_desc_sw128(ptx::smem_u32(sP + 2 * TILE_BYTES)),
-                     pB1 = ptx::smem_desc_sw128(ptx::smem_u32(sP + 3 * TILE_BYTES));
-      const uint32_t tSA = tmem_base, tSB = tmem_base + 128, tOA = tmem_base + 256, tOB = tmem_base + 320;
-      auto kdesc = [&](int t) { return ptx::smem_desc_sw128(ptx::smem_u32(sK + (t % PAIR_KV_STAGES) * TILE_BYTES)); };
-      auto vdesc = [&](int t) { return ptx::smem_desc_sw128(ptx::smem_u32(sV + (t % PAIR_KV_STAGES) * TILE_BYTES)); };
-      ptx::mbar_wait(q_full, 0);
-      ptx::mbar_wait(kv_full0, 0);
-      ptx::tc_fence_after();
-      issue_qk(tSA, qdA, kdesc(0));
+    // MMA issuer: warp-uniform loop, one elected lane issues (see ptx::elect_one)
+    const uint64_t qdA = ptx::smem_desc_sw128(ptx::smem_u32(sQ)), qdB = ptx::smem_desc_sw128(ptx::smem_u32(sQ + TILE_BYTES));
+    const uint64_t pA0 = ptx::smem_desc_sw128(ptx::smem_u32(sP)), pA1 = ptx::smem_desc_sw128(ptx::smem_u32(sP + TILE_BYTES));
+    const uint64_t pB0 = ptx::smem_desc_sw128(ptx::smem_u32(sP + 2 * TILE_BYTES)),
+                   pB1 = ptx::smem_desc_sw128(ptx::smem_u32(sP + 3 * TILE_BYTES));
+    const uint32_t tSA = tmem_base, tSB = tmem_base + 128, tOA = tmem_base + 256, tOB = tmem_base + 320;
+    const uint64_t k0 = ptx::smem_desc_sw128(ptx::smem_u32(sK)), v0 = ptx::smem_desc_sw128(ptx::smem_u32(sV));
+    constexpr uint64_t STAGE_DESC = TILE_BYTES >> 4;  // descriptor start-address units per K/V stage
+    ptx::mbar_wait(q_full, 0);
+    ptx::mbar_wait(kv_full0, 0);
+    ptx::tc_fence_after();
+    if (ptx::elect_one()) {
+      issue_qk(tSA, qdA, k0);
       ptx::mma_commit(s_full0);
-      for (int j = 0; j <= n_tiles; ++j) {
-        if (j < n_tiles) {
-          // ---- tile A, KV tile j: O_A += P_A(j) V(j); then S_A(j+1) so warpgroup A can start its next softmax at once
-          ptx::mbar_wait(p_full0, j & 1);
-          ptx::tc_fence_after();
-          issue_pv(tOA, pA0, pA1, vdesc(j), j == 0);
+    }
+    __syncwarp();
+    for (int j = 0; j <= n_tiles; ++j) {
+      const uint64_t kd_j = k0 + (uint64_t)(j % PAIR_KV_STAGES) * STAGE_DESC, kd_n = k0 + (uint64_t)((j + 1) % PAIR_KV_STAGES) * STAGE_DESC;
+      const uint64_t vd_j = v0 + (uint64_t)(j % PAIR_KV_STAGES) * STAGE_DESC;
+      const uint64_t vd_p = v0 + (uint64_t)((j + PAIR_KV_STAGES - 1) % PAIR_KV_STAGES) * STAGE_DESC;
+      if (j < n_tiles) {
+        // ---- tile A, KV tile j: O_A += P_A(j) V(j); then S_A(j+1) so warpgroup A can start its next softmax at once
+        ptx::mbar_wait(p_full0, j & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          issue_pv(tOA, pA0, pA1, vd_j, j == 0);
           ptx::mma_commit(o_ready0);
-          if (j + 1 < n_tiles) {
-            ptx::mbar_wait(kv_full0 + 8 * ((j + 1) % PAIR_KV_STAGES), ((j + 1) / PAIR_KV_STAGES) & 1);
-            ptx::tc_fence_after();
-            issue_qk(tSA, qdA, kdesc(j + 1));
+        }
+        __syncwarp();
+        if (j + 1 < n_tiles) {
+          ptx::mbar_wait(kv_full0 + 8 * ((j + 1) % PAIR_KV_STAGES), ((j + 1) / PAIR_KV_STAGES) & 1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            issue_qk(tSA, qdA, kd_n);
             ptx::mma_commit(s_full0);
           }
+          __syncwarp();
         }
-        // ---- tile B, one KV tile behind
-        if (j > 0) {
+      }
+      // ---- tile B, one KV tile behind
+      if (j > 0) {
+        if (has_b) {
+          ptx::mbar_wait(p_full0 + 8, (j - 1) & 1);
+          ptx::tc_fence_after();
+        }
+        if (ptx::elect_one()) {
           if (has_b) {
-            ptx::mbar_wait(p_full0 + 8, (j - 1) & 1);
-            ptx::tc_fence_after();
-            issue_pv(tOB, pB0, pB1, vdesc(j - 1), j == 1);
+            issue_pv(tOB, pB0, pB1, vd_p, j == 1);
             ptx::mma_commit(o_ready0 + 8);
           }
           ptx::mma_commit(kv_empty0 + 8 * ((j - 1) % PAIR_KV_STAGES));  // both query tiles are done with KV tile j-1
         }
-        if (has_b && j < n_tiles) {
-          issue_qk(tSB, qdB, kdesc(j));  // kv_full(j) was already observed for tile A
+        __syncwarp();
+      }
+      if (has_b && j < n_tiles) {
+        if (ptx::elect_one()) {
+          issue_qk(tSB, qdB, kd_j);  // kv_full(j) was already observed for tile A
           ptx::mma_commit(s_full0 + 8);
         }
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -501,6 +553,7 @@ extern "C" int ladi_attention_bf16(const ladi_attn_desc* d, void* stream_) {
   p.nq = d->nq; p.nkv = d->nkv; p.n_kv_tiles = (d->nkv + BKV - 1) / BKV;
   p.out = reinterpret_cast<bf16*>(d->out); p.out_pitch = d->out_pitch; p.out_batch_stride = d->out_batch_stride;
   p.scale_log2 = d->scale * 1.4426950408889634f;
+  p.trace = reinterpret_cast<long long*>(d->trace);
   static bool attr_set = false;
   if (!attr_set) {
     LADI_CUDA(cudaFuncSetAttribute(attention_single_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE));

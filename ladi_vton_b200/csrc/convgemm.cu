@@ -145,55 +145,57 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
   const int num_items = num_tiles * p.splits;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ TMA producer
-      uint32_t stage = 0, phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int tile = item / p.splits, split = item - tile * p.splits;
-        const int kb0 = split * p.kb_per_split, kb1 = min(p.total_kb, kb0 + p.kb_per_split);
-        const TileCoord tc = tile_coord(p, tile);
-        int kb = 0;
-        for (int s = 0; s < p.nseg && kb < kb1; ++s) {
-          const Segment sg = p.seg[s];
-          const CUtensorMap* am = &amaps.m[sg.map];
-          if (kb + sg.chunks <= kb0) { kb += sg.chunks; continue; }
-          for (int c = 0; c < sg.chunks && kb < kb1; ++c, ++kb) {
-            if (kb < kb0) continue;
-            ptx::mbar_wait(empty0 + 8 * stage, phase ^ 1);
-            const uint32_t fb = full0 + 8 * stage;
+    // ------------------------------------------------------------------ TMA producer (warp-uniform loop, one elected lane issues)
+    uint32_t stage = 0, phase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int tile = item / p.splits, split = item - tile * p.splits;
+      const int kb0 = split * p.kb_per_split, kb1 = min(p.total_kb, kb0 + p.kb_per_split);
+      const TileCoord tc = tile_coord(p, tile);
+      int kb = 0;
+      for (int s = 0; s < p.nseg && kb < kb1; ++s) {
+        const Segment sg = p.seg[s];
+        const CUtensorMap* am = &amaps.m[sg.map];
+        if (kb + sg.chunks <= kb0) { kb += sg.chunks; continue; }
+        for (int c = 0; c < sg.chunks && kb < kb1; ++c, ++kb) {
+          if (kb < kb0) continue;
+          ptx::mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          const uint32_t fb = full0 + 8 * stage;
+          if (ptx::elect_one()) {
             ptx::mbar_expect_tx(fb, A_BYTES + B_BYTES);
             ptx::tma_load_4d(am, ptx::smem_u32(sA + stage * A_BYTES), fb, sg.c_begin + c * BK, tc.x0 + sg.dx, tc.y0 + sg.dy, tc.n0);
             ptx::tma_load_2d(&tmB, ptx::smem_u32(sB + stage * B_BYTES), fb, kb * BK, tc.nt * BN);
-            if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ MMA issuer (single thread)
-      constexpr uint32_t idesc = ptx::idesc_bf16(BM, BN, 0, 0);
-      uint32_t stage = 0, phase = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-        const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-        const int split = item % p.splits;
-        const int nkb = min(p.total_kb, (split + 1) * p.kb_per_split) - split * p.kb_per_split;
-        ptx::mbar_wait(tempty0 + 8 * as, aphase ^ 1);
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
+    constexpr uint32_t idesc = ptx::idesc_bf16(BM, BN, 0, 0);
+    uint32_t stage = 0, phase = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+      const int split = item % p.splits;
+      const int nkb = min(p.total_kb, (split + 1) * p.kb_per_split) - split * p.kb_per_split;
+      ptx::mbar_wait(tempty0 + 8 * as, aphase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
+      for (int kb = 0; kb < nkb; ++kb) {
+        ptx::mbar_wait(full0 + 8 * stage, phase);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
-        for (int kb = 0; kb < nkb; ++kb) {
-          ptx::mbar_wait(full0 + 8 * stage, phase);
-          ptx::tc_fence_after();
-          const uint64_t adesc = ptx::smem_desc_sw128(ptx::smem_u32(sA + stage * A_BYTES));
-          const uint64_t bdesc = ptx::smem_desc_sw128(ptx::smem_u32(sB + stage * B_BYTES));
+        const uint64_t adesc = ptx::smem_desc_sw128(ptx::smem_u32(sA + stage * A_BYTES));
+        const uint64_t bdesc = ptx::smem_desc_sw128(ptx::smem_u32(sB + stage * B_BYTES));
+        if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k)
             ptx::mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           ptx::mma_commit(empty0 + 8 * stage);  // smem slot reusable once these MMAs have read it
-          if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
+          if (kb == nkb - 1) ptx::mma_commit(tfull0 + 8 * as);  // accumulator complete
         }
-        ptx::mma_commit(tfull0 + 8 * as);  // accumulator complete
+        __syncwarp();
+        if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp >= 4) {

@@ -14,6 +14,20 @@ namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully converged warp.  The TMA / tcgen05 issuer warps run their loops with ALL lanes (warp-uniform control
+// flow, so descriptors, coordinates and barrier addresses live in uniform registers) and guard only the asynchronous
+// instructions with elect_one(): issuing from inside a divergent `if (lane == 0)` costs a chain of R2UR moves per instruction
+// (measured ~65 cycles per tcgen05.mma, which starves MMAs that execute in 32-80 cycles).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

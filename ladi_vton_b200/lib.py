@@ -32,7 +32,7 @@ class AttnDesc(C.Structure):
         ("k", C.c_void_p), ("k_pitch", C.c_int), ("k_batch_stride", C.c_int64),
         ("v", C.c_void_p), ("v_pitch", C.c_int), ("v_batch_stride", C.c_int64),
         ("out", C.c_void_p), ("out_pitch", C.c_int), ("out_batch_stride", C.c_int64),
-        ("scale", C.c_float), ("variant", C.c_int),
+        ("scale", C.c_float), ("variant", C.c_int), ("trace", C.c_void_p),
     ]
 
 

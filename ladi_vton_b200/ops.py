@@ -132,7 +132,7 @@ def gemm(a, weight, n_out, **kw):
     return o[0, 0]
 
 
-def attention(q, k, v, heads, scale, out=None, variant=0):
+def attention(q, k, v, heads, scale, out=None, variant=0, trace=None):
     """q [B, Nq, >=heads*64] , k/v [B, Nkv, >=heads*64] (row-strided views of fused projections are fine) -> [B, Nq, heads*64]."""
     B, nq = q.shape[0], q.shape[1]
     nkv = k.shape[1]
@@ -148,6 +148,7 @@ def attention(q, k, v, heads, scale, out=None, variant=0):
     d.out, d.out_pitch, d.out_batch_stride = out.data_ptr(), out.stride(1), out.stride(0)
     d.scale = scale
     d.variant = variant
+    d.trace = trace.data_ptr() if trace is not None else 0
     _call("ladi_attention_bf16", 4.0 * B * heads * nq * nkv * 64, C.byref(d), _stream(), tag=f"B={B} heads={heads} nq={nq} nkv={nkv}")
     return out
 

@@ -49,10 +49,10 @@ __device__ __forceinline__ float ex2(float x) {
 // columns of every S tile, the O columns and the P K-chunks, and agree on the running row maximum through shared memory).
 // Consumes S tiles from TMEM, produces P tiles in shared memory, keeps O normalised.
 //   S for KV tile j lives at tS + s_stride * (j & s_mask); barriers: s_full (per S buffer), p_full (count 128*HALVES), o_ready.
-template <int HALVES, bool SINGLE_READ>
+template <int HALVES, bool SINGLE_READ, bool PT = false>
 __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, uint32_t tS, uint32_t s_stride, uint32_t s_mask, uint32_t tO,
                                              uint8_t* sP, uint32_t s_full0, uint32_t p_full, uint32_t o_ready, int ew, int lane, int q0,
-                                             int h, int b, int half, float* xm, uint32_t bar_id) {
+                                             int h, int b, int half, float* xm, uint32_t bar_id, uint32_t tP = 0) {
   constexpr int COLS = BKV / HALVES;        // key columns of each S tile owned by this thread
   constexpr int OCOLS = HD / HALVES;        // O columns owned by this thread
   const int r = ew * 32 + lane;
@@ -206,10 +206,18 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
       ptx::tc_fence_after();
     }
     TRACE(5);
+    if constexpr (PT) {  // P goes to tensor memory (A operand of the PV MMA): lane = row, 2 bf16 per column, COLS/2 columns
+      static_assert(COLS == 64 || COLS == 128, "P tile chunks of 32 packed columns");
+#pragma unroll
+      for (int c = 0; c < COLS / 2; c += 32)
+        ptx::tmem_st32(tP + lane_off + half * (COLS / 2) + c, reinterpret_cast<const uint32_t(&)[32]>(pk[c]));
+      ptx::tmem_wait_st();
+    } else {
 #pragma unroll
     for (int q = 0; q < COLS / 8; ++q) {  // 16-byte pieces: 8 per 64-key chunk, XOR-swizzled by (row & 7)
       uint8_t* dst = prow0 + (q >> 3) * TILE_BYTES + (((q & 7) ^ sw) << 4);
       *reinterpret_cast<uint4*>(dst) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
     }
     }
     if (j > 0 && __any_sync(0xffffffffu, moved)) {
@@ -226,7 +234,7 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
     }
     TRACE(6);
     ptx::tc_fence_before();
-    ptx::fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor core (async proxy)
+    if constexpr (!PT) ptx::fence_proxy_async_smem();  // generic-proxy P writes -> visible to the tensor core (async proxy)
     ptx::mbar_arrive(p_full);
     TRACE(7);
   }
@@ -271,6 +279,12 @@ __device__ __forceinline__ void issue_pv(uint32_t tO, uint64_t pdesc0, uint64_t 
 #pragma unroll
   for (int k = 0; k < BKV / 16; ++k)
     ptx::mma_ss(tO, (k < 4 ? pdesc0 + 2 * k : pdesc1 + 2 * (k - 4)), vdesc + 128 * k, idesc_pv, (!first) || (k != 0));
+}
+
+__device__ __forceinline__ void issue_pv_ts(uint32_t tO, uint32_t tP, uint64_t vdesc, int first) {
+  constexpr uint32_t idesc_pv = ptx::idesc_bf16(128, HD, 0, 1);  // A = P from tensor memory (K-major), B = V MN-major
+#pragma unroll
+  for (int k = 0; k < BKV / 16; ++k) ptx::mma_ts(tO, tP + 8 * k, vdesc + 128 * k, idesc_pv, (!first) || (k != 0));
 }
 
 // ============================================================================================ one query tile per CTA
@@ -383,7 +397,7 @@ attention_single_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 // versa, so MMA latency is hidden instead of being added to every iteration.  K/V ring of 3 stages (tile t is needed from
 // S_A(t), issued in iteration t-1, until PV_B(t), issued in iteration t+1).
 constexpr int PAIR_KV_STAGES = 3;
-template <bool SR>
+template <bool SR, bool PT>
 __global__ void __launch_bounds__(640, 1)
 attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
@@ -452,6 +466,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const uint64_t pB0 = ptx::smem_desc_sw128(ptx::smem_u32(sP + 2 * TILE_BYTES)),
                    pB1 = ptx::smem_desc_sw128(ptx::smem_u32(sP + 3 * TILE_BYTES));
     const uint32_t tSA = tmem_base, tSB = tmem_base + 128, tOA = tmem_base + 256, tOB = tmem_base + 320;
+    const uint32_t tPA = tmem_base + 384, tPB = tmem_base + 448;  // P tiles in tensor memory (PT variant)
     const uint64_t k0 = ptx::smem_desc_sw128(ptx::smem_u32(sK)), v0 = ptx::smem_desc_sw128(ptx::smem_u32(sV));
     constexpr uint64_t STAGE_DESC = TILE_BYTES >> 4;  // descriptor start-address units per K/V stage
     ptx::mbar_wait(q_full, 0);
@@ -471,7 +486,8 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         ptx::mbar_wait(p_full0, j & 1);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
-          issue_pv(tOA, pA0, pA1, vd_j, j == 0);
+          if constexpr (PT) issue_pv_ts(tOA, tPA, vd_j, j == 0);
+          else issue_pv(tOA, pA0, pA1, vd_j, j == 0);
           ptx::mma_commit(o_ready0);
         }
         __syncwarp();
@@ -493,7 +509,8 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
         if (ptx::elect_one()) {
           if (has_b) {
-            issue_pv(tOB, pB0, pB1, vd_p, j == 1);
+            if constexpr (PT) issue_pv_ts(tOB, tPB, vd_p, j == 1);
+            else issue_pv(tOB, pB0, pB1, vd_p, j == 1);
             ptx::mma_commit(o_ready0 + 8);
           }
           ptx::mma_commit(kv_empty0 + 8 * ((j - 1) % PAIR_KV_STAGES));  // both query tiles are done with KV tile j-1
@@ -512,8 +529,9 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int wg = (warp - 4) >> 3;         // 0 = tile A (warps 4-11), 1 = tile B (warps 12-19)
     const int half = ((warp - 4) >> 2) & 1;  // which half of the key columns / O columns this warpgroup owns
     if (wg == 0 || has_b)
-      softmax_rows<2, SR>(p, n_tiles, tmem_base + 128 * wg, 0, 0u, tmem_base + 256 + 64 * wg, sP + wg * 2 * TILE_BYTES, s_full0 + 8 * wg,
-                      p_full0 + 8 * wg, o_ready0 + 8 * wg, warp & 3, lane, (qp * 2 + wg) * BQ, h, b, half, xm + wg * 512, 1 + wg);
+      softmax_rows<2, SR, PT>(p, n_tiles, tmem_base + 128 * wg, 0, 0u, tmem_base + 256 + 64 * wg, sP + wg * 2 * TILE_BYTES, s_full0 + 8 * wg,
+                          p_full0 + 8 * wg, o_ready0 + 8 * wg, warp & 3, lane, (qp * 2 + wg) * BQ, h, b, half, xm + wg * 512, 1 + wg,
+                          tmem_base + 384 + 64 * wg);
   }
 
   __syncwarp();
@@ -558,11 +576,12 @@ extern "C" int ladi_attention_bf16(const ladi_attn_desc* d, void* stream_) {
   if (!attr_set) {
     LADI_CUDA(cudaFuncSetAttribute(attention_single_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE));
     LADI_CUDA(cudaFuncSetAttribute(attention_single_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SHORT));
-    LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
-    LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
+    LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
+    LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
+    LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
     attr_set = true;
   }
-  const int variant = d->variant;  // 0 auto, 1 single, 2 pair (two TMEM passes), 3 pair (single TMEM read) (tests / tuning)
+  const int variant = d->variant;  // 0 auto, 1 single, 2 pair (P in smem), 3 pair (single TMEM read), 4 pair (P in tensor memory) (tests / tuning)
   if ((variant == 0 && d->nkv <= BKV) || (variant == 1 && d->nkv <= BKV)) {
     dim3 grid((d->nq + BQ - 1) / BQ, d->heads, d->batch);
     LADI_CUDA(ladi_launch(attention_single_kernel<true>, grid, dim3(256), SMEM_SHORT, stream, tq, tk, tv, p));
@@ -571,8 +590,9 @@ extern "C" int ladi_attention_bf16(const ladi_attn_desc* d, void* stream_) {
     LADI_CUDA(ladi_launch(attention_single_kernel<false>, grid, dim3(256), SMEM_SINGLE, stream, tq, tk, tv, p));
   } else {
     dim3 grid((d->nq + 2 * BQ - 1) / (2 * BQ), d->heads, d->batch);
-    if (variant == 3) LADI_CUDA(ladi_launch(attention_pair_kernel<true>, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
-    else LADI_CUDA(ladi_launch(attention_pair_kernel<false>, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
+    if (variant == 3) LADI_CUDA(ladi_launch(attention_pair_kernel<true, false>, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
+    else if (variant == 4) LADI_CUDA(ladi_launch(attention_pair_kernel<false, true>, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
+    else LADI_CUDA(ladi_launch(attention_pair_kernel<false, false>, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
   }
   return LADI_OK;
 }

@@ -8,7 +8,7 @@ dev = torch.device("cuda:0")
 q = torch.randn((16, 3072, 960), device=dev).bfloat16()
 tr = torch.zeros(8192, dtype=torch.int64, device=dev)
 for _ in range(2):
-    ops.attention(q[..., :320], q[..., 320:640], q[..., 640:], 5, 0.125, variant=2, trace=tr)
+    ops.attention(q[..., :320], q[..., 320:640], q[..., 640:], 5, 0.125, variant=int(sys.argv[1]) if len(sys.argv) > 1 else 2, trace=tr)
 torch.cuda.synchronize()
 t = tr.cpu().numpy().astype("int64")
 t0 = t[t > 0].min()

@@ -581,8 +581,10 @@ extern "C" int ladi_attention_bf16(const ladi_attn_desc* d, void* stream_) {
     LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
     attr_set = true;
   }
-  const int variant = d->variant;  // 0 auto, 1 single, 2 pair (P in smem), 3 pair (single TMEM read), 4 pair (P in tensor memory) (tests / tuning)
-  if ((variant == 0 && d->nkv <= BKV) || (variant == 1 && d->nkv <= BKV)) {
+  // variant: 0 auto, 1 one query tile per CTA, 2 pair (P in smem), 3 pair (single TMEM read), 4 pair (P in tensor memory)
+  int variant = d->variant;
+  if (variant == 0) variant = (d->nkv <= BKV) ? 1 : (d->nq >= 2048 ? 4 : 1);  // measured: the pair kernel wins only on long sequences
+  if (variant == 1 && d->nkv <= BKV) {
     dim3 grid((d->nq + BQ - 1) / BQ, d->heads, d->batch);
     LADI_CUDA(ladi_launch(attention_single_kernel<true>, grid, dim3(256), SMEM_SHORT, stream, tq, tk, tv, p));
   } else if (variant == 1) {

@@ -155,3 +155,49 @@ def test_inversion_adapter_full(cuda):
     err = rel_l2(y, ref)
     print("inversion adapter rel-L2 vs fp32 oracle:", err)
     assert err < 2e-2
+
+
+@pytest.mark.parametrize("opts", [dict(no_pose=True), dict(cloth_cond_rate=0.4), dict(batch=1, guidance_scale=7.5), dict(latents=True),
+                                  dict(callback=True), dict(num_inference_steps=1)])
+def test_pipeline_options_small(cuda, small, opts):
+    """Less-travelled arguments of `__call__` (tryon_pipe.py:495-520): no_pose, cloth_cond_rate < 1 (cloth latents zeroed for the
+    last steps, :718-719), batch 1, caller-supplied latents, per-step callback (disables graph replay), a single step."""
+    from ladi_vton_b200 import synthetic as S
+    from ladi_oracle.parts import DDIMScheduler
+    from ladi_oracle.pipeline import OracleTryOnPipeline
+    pipe, ou, ov, oe = small
+    opts = dict(opts)
+    B = opts.pop("batch", 2)
+    steps = opts.pop("num_inference_steps", 5)
+    gs = opts.pop("guidance_scale", 7.5)
+    inp = S.synthetic_inputs(B, 128, 64, ctx_dim=128)
+    kw = {k: v for k, v in opts.items() if k in ("no_pose", "cloth_cond_rate")}
+    lat = torch.randn((B, 4, 16, 8), generator=torch.Generator().manual_seed(3)) if opts.get("latents") else None
+    op = OracleTryOnPipeline(ov, ou, DDIMScheduler(), oe, [1, 2, 3, 4, 5])
+    ref = op(inp["image"].clone(), inp["mask_image"].clone(), inp["pose_map"], inp["warped_cloth"], inp["prompt_embeds"],
+             inp["negative_prompt_embeds"], height=128, width=64, num_inference_steps=steps, guidance_scale=gs,
+             generator=torch.Generator().manual_seed(7), latents=None if lat is None else lat.clone(), **kw)
+    seen = []
+    cb = (lambda i, t, l: seen.append((i, int(t), tuple(l.shape)))) if opts.get("callback") else None
+    pipe.use_cuda_graph = True
+    out = pipe(image=inp["image"].clone(), mask_image=inp["mask_image"].clone(), pose_map=inp["pose_map"], warped_cloth=inp["warped_cloth"],
+               prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"], height=128, width=64,
+               num_inference_steps=steps, guidance_scale=gs, generator=torch.Generator().manual_seed(7), output_type="np",
+               latents=lat, callback=cb, **kw).images
+    assert out.shape == ref.shape
+    mad = np.abs(out - ref).mean() * 255
+    print(f"pipeline options {opts or dict(batch=B, steps=steps)}: mean|engine-oracle| = {mad:.3f}/255")
+    assert mad < 2.0
+    if cb is not None:
+        assert [s[0] for s in seen] == list(range(steps)) and seen[0][1] == 801 and seen[0][2] == (B, 4, 16, 8)
+
+
+def test_pipeline_pil_output_and_tuple(cuda, small):
+    from ladi_vton_b200 import synthetic as S
+    pipe = small[0]
+    inp = S.synthetic_inputs(1, 128, 64, ctx_dim=128)
+    res = pipe(image=inp["image"], mask_image=inp["mask_image"], pose_map=inp["pose_map"], warped_cloth=inp["warped_cloth"],
+               prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"], height=128, width=64,
+               num_inference_steps=2, generator=torch.Generator().manual_seed(7), return_dict=False)
+    imgs, nsfw = res
+    assert nsfw is None and len(imgs) == 1 and imgs[0].size == (64, 128) and imgs[0].mode == "RGB"  # PIL (W, H), tryon_pipe.py:759-765

@@ -33,11 +33,17 @@ struct AttnParams {
   long long* trace;  // optional per-phase clock64() trace of CTA (0,0,0) (tools/attn_trace.py); null in production
 };
 
+#ifdef LADI_ATTN_TRACE  // debug builds only (tools/attn_trace.py): per-phase clock64() stamps of CTA (0,0,0)
 #define TRACE(slot)                                                                         \
   do {                                                                                      \
     if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && trace_ok) \
       p.trace[trace_base + (slot)] = clock64();                                             \
   } while (0)
+#else
+#define TRACE(slot) \
+  do {              \
+  } while (0)
+#endif
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -269,6 +275,129 @@ __device__ __forceinline__ void softmax_rows(const AttnParams& p, int n_tiles, u
   }
 }
 
+// Production softmax of the pair kernel: two threads per query row (64 key columns each), P to tensor memory, and a LAZY
+// reference maximum: tile 0 takes an exact row maximum (two TMEM passes); every later tile is ONE pass that scales with the
+// reference m carried over from earlier tiles while tracking its own maximum; m is only raised (and O, l rescaled) at tile
+// boundaries when the running maximum outgrew it by more than 2^8.  O / l is invariant to m, and P <= 2^(growth) stays far inside
+// bf16 / fp32 range, so the result equals the exact online softmax up to rounding.
+__device__ __forceinline__ void softmax_pair_lazy(const AttnParams& p, int n_tiles, uint32_t tS, uint32_t tO, uint32_t tP, uint32_t s_full,
+                                                  uint32_t p_full, uint32_t o_ready, int ew, int lane, int q0, int h, int b, int half,
+                                                  float* xm, uint32_t bar_id) {
+  constexpr int COLS = BKV / 2, OCOLS = HD / 2;
+  const int r = ew * 32 + lane;
+  const uint32_t lane_off = (uint32_t)(ew * 32) << 16;
+  const int col0 = half * COLS;
+  const uint32_t ts = tS + lane_off + col0;
+  float m = -INFINITY, l = 0.f, alpha_pending = 1.f;
+  bool rescale_pending = false;
+  for (int j = 0; j < n_tiles; ++j) {
+    const int valid = min(COLS, p.nkv - j * BKV - col0);  // may be <= 0 for the upper half of a ragged last tile
+    ptx::mbar_wait(s_full, j & 1);
+    ptx::tc_fence_after();
+    if (j == 0) {  // exact maximum for the first tile
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < COLS; c += 32) {
+        if (c >= valid) break;
+        uint32_t v[32];
+        ptx::tmem_ld32(ts + c, v);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      xm[half * 128 + r] = mx;
+      ptx::named_barrier_sync(bar_id, 256);
+      m = fmaxf(mx, xm[(half ^ 1) * 128 + r]) * p.scale_log2;
+    }
+    // The tensor pipe completes MMAs in issue order and S(j) was issued after P(j-1) V: s_full(j) therefore also means
+    // that O and the P region are free again -- no separate wait on o_ready inside the loop.
+    if (j > 0 && __any_sync(0xffffffffu, rescale_pending)) {  // the reference moved at the last boundary: bring O to the new scale
+      uint32_t v[32];
+      ptx::tmem_ld32(tO + lane_off + half * OCOLS, v);
+      ptx::tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha_pending);
+      ptx::tmem_st32(tO + lane_off + half * OCOLS, v);
+    }
+    // ---- one pass: p = exp2(s*scale - m) packed to bf16 and streamed to tensor memory 32 keys at a time, plus this tile's own
+    // maximum for the next reference
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    float x0 = -INFINITY, x1 = -INFINITY, x2 = -INFINITY, x3 = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < COLS; c += 32) {
+      uint32_t v[32], pk[16];
+      if (c < valid) {
+        ptx::tmem_ld32(ts + c, v);
+        ptx::tmem_wait_ld();
+      }
+      if (c + 32 <= valid) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float a0 = __uint_as_float(v[i]), a1 = __uint_as_float(v[i + 1]), a2 = __uint_as_float(v[i + 2]), a3 = __uint_as_float(v[i + 3]);
+          x0 = fmaxf(x0, a0); x1 = fmaxf(x1, a1); x2 = fmaxf(x2, a2); x3 = fmaxf(x3, a3);
+          const float p0 = ex2(fmaf(a0, p.scale_log2, -m)), p1 = ex2(fmaf(a1, p.scale_log2, -m));
+          const float p2 = ex2(fmaf(a2, p.scale_log2, -m)), p3 = ex2(fmaf(a3, p.scale_log2, -m));
+          s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+          pk[i >> 1] = ptx::pack_bf16(p0, p1);
+          pk[(i >> 1) + 1] = ptx::pack_bf16(p2, p3);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = 0.f, p1 = 0.f;
+          if (c + i < valid) { const float a = __uint_as_float(v[i]); x0 = fmaxf(x0, a); p0 = ex2(fmaf(a, p.scale_log2, -m)); }
+          if (c + i + 1 < valid) { const float a = __uint_as_float(v[i + 1]); x1 = fmaxf(x1, a); p1 = ex2(fmaf(a, p.scale_log2, -m)); }
+          s0 += p0; s1 += p1;
+          pk[i >> 1] = ptx::pack_bf16(p0, p1);
+        }
+      }
+      ptx::tmem_st16(tP + lane_off + half * (COLS / 2) + (c >> 1), pk);
+    }
+    l += (s0 + s1) + (s2 + s3);
+    ptx::tmem_wait_st();
+    ptx::tc_fence_before();
+    ptx::mbar_arrive(p_full);
+    // ---- off the MMA critical path: agree on the reference for the next tile
+    if (j + 1 < n_tiles) {
+      float* slot = xm + ((j + 1) & 1) * 256;
+      const float mxl = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
+      slot[half * 128 + r] = mxl;
+      ptx::named_barrier_sync(bar_id, 256);
+      const float m_true = fmaxf(mxl, slot[(half ^ 1) * 128 + r]) * p.scale_log2;
+      rescale_pending = m_true > m + 8.f;
+      alpha_pending = rescale_pending ? ex2(m - m_true) : 1.f;
+      if (rescale_pending) { l *= alpha_pending; m = m_true; }
+    }
+  }
+  // ---- output: O / l, row sum = sum over both column halves (identical references throughout)
+  {
+    float* slot = xm + ((n_tiles + 1) & 1) * 256;
+    slot[half * 128 + r] = l;
+    ptx::named_barrier_sync(bar_id, 256);
+    l += slot[(half ^ 1) * 128 + r];
+  }
+  ptx::mbar_wait(o_ready, (n_tiles - 1) & 1);
+  ptx::tc_fence_after();
+  const int qi = q0 + r;
+  const float inv = 1.f / l;
+  bf16* orow = p.out + (size_t)b * p.out_batch_stride + (size_t)qi * p.out_pitch + h * HD + half * OCOLS;
+  uint32_t v[32];
+  ptx::tmem_ld32(tO + lane_off + half * OCOLS, v);
+  ptx::tmem_wait_ld();
+  if (qi < p.nq) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      uint4 u;
+      u.x = ptx::pack_bf16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+      u.y = ptx::pack_bf16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+      u.z = ptx::pack_bf16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+      u.w = ptx::pack_bf16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+      *reinterpret_cast<uint4*>(orow + i) = u;
+    }
+  }
+}
+
 __device__ __forceinline__ void issue_qk(uint32_t tS, uint64_t qdesc, uint64_t kdesc) {
   constexpr uint32_t idesc_qk = ptx::idesc_bf16(128, BKV, 0, 0);
 #pragma unroll
@@ -397,7 +526,7 @@ attention_single_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 // versa, so MMA latency is hidden instead of being added to every iteration.  K/V ring of 3 stages (tile t is needed from
 // S_A(t), issued in iteration t-1, until PV_B(t), issued in iteration t+1).
 constexpr int PAIR_KV_STAGES = 3;
-template <bool SR, bool PT>
+template <bool SR, bool PT, bool LAZY = false>
 __global__ void __launch_bounds__(640, 1)
 attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
@@ -438,9 +567,8 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)
+  // TMEM columns: S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)  P_A [384,448)  P_B [448,512)
   ptx::pdl_wait();
-
   if (warp == 0) {
     if (ptx::elect_one()) {
       ptx::mbar_expect_tx(q_full, (has_b ? 2 : 1) * TILE_BYTES);
@@ -528,10 +656,15 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   } else if (warp >= 4) {
     const int wg = (warp - 4) >> 3;         // 0 = tile A (warps 4-11), 1 = tile B (warps 12-19)
     const int half = ((warp - 4) >> 2) & 1;  // which half of the key columns / O columns this warpgroup owns
-    if (wg == 0 || has_b)
-      softmax_rows<2, SR, PT>(p, n_tiles, tmem_base + 128 * wg, 0, 0u, tmem_base + 256 + 64 * wg, sP + wg * 2 * TILE_BYTES, s_full0 + 8 * wg,
-                          p_full0 + 8 * wg, o_ready0 + 8 * wg, warp & 3, lane, (qp * 2 + wg) * BQ, h, b, half, xm + wg * 512, 1 + wg,
-                          tmem_base + 384 + 64 * wg);
+    if (wg == 0 || has_b) {
+      if constexpr (LAZY)
+        softmax_pair_lazy(p, n_tiles, tmem_base + 128 * wg, tmem_base + 256 + 64 * wg, tmem_base + 384 + 64 * wg, s_full0 + 8 * wg,
+                          p_full0 + 8 * wg, o_ready0 + 8 * wg, warp & 3, lane, (qp * 2 + wg) * BQ, h, b, half, xm + wg * 512, 1 + wg);
+      else
+        softmax_rows<2, SR, PT>(p, n_tiles, tmem_base + 128 * wg, 0, 0u, tmem_base + 256 + 64 * wg, sP + wg * 2 * TILE_BYTES, s_full0 + 8 * wg,
+                                p_full0 + 8 * wg, o_ready0 + 8 * wg, warp & 3, lane, (qp * 2 + wg) * BQ, h, b, half, xm + wg * 512, 1 + wg,
+                                tmem_base + 384 + 64 * wg);
+    }
   }
 
   __syncwarp();
@@ -577,13 +710,13 @@ extern "C" int ladi_attention_bf16(const ladi_attn_desc* d, void* stream_) {
     LADI_CUDA(cudaFuncSetAttribute(attention_single_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE));
     LADI_CUDA(cudaFuncSetAttribute(attention_single_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SHORT));
     LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
-    LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
     LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
+    LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
     attr_set = true;
   }
-  // variant: 0 auto, 1 one query tile per CTA, 2 pair (P in smem), 3 pair (single TMEM read), 4 pair (P in tensor memory)
+  // variant: 0 auto, 1 one query tile per CTA, 2 pair (P in smem), 4 pair (P in tensor memory), 5 pair (P in TMEM + lazy single-pass softmax)
   int variant = d->variant;
-  if (variant == 0) variant = (d->nkv <= BKV) ? 1 : (d->nq >= 2048 ? 4 : 1);  // measured: the pair kernel wins only on long sequences
+  if (variant == 0) variant = (d->nkv <= BKV || d->nq < 512) ? 1 : 5;  // measured: the pair kernel wins from ~512 queries up
   if (variant == 1 && d->nkv <= BKV) {
     dim3 grid((d->nq + BQ - 1) / BQ, d->heads, d->batch);
     LADI_CUDA(ladi_launch(attention_single_kernel<true>, grid, dim3(256), SMEM_SHORT, stream, tq, tk, tv, p));
@@ -592,8 +725,8 @@ extern "C" int ladi_attention_bf16(const ladi_attn_desc* d, void* stream_) {
     LADI_CUDA(ladi_launch(attention_single_kernel<false>, grid, dim3(256), SMEM_SINGLE, stream, tq, tk, tv, p));
   } else {
     dim3 grid((d->nq + 2 * BQ - 1) / (2 * BQ), d->heads, d->batch);
-    if (variant == 3) LADI_CUDA(ladi_launch(attention_pair_kernel<true, false>, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
-    else if (variant == 4) LADI_CUDA(ladi_launch(attention_pair_kernel<false, true>, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
+    if (variant == 4) LADI_CUDA(ladi_launch(attention_pair_kernel<false, true>, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
+    else if (variant == 5) LADI_CUDA(ladi_launch(attention_pair_kernel<false, true, true>, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
     else LADI_CUDA(ladi_launch(attention_pair_kernel<false, false>, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
   }
   return LADI_OK;

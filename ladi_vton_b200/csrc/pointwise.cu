@@ -61,7 +61,20 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
       float s[8], q[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-      for (int px = p0 + tp; px < p1; px += k) {
+      int px = p0 + tp;
+      for (; px + 3 * k < p1; px += 4 * k) {  // 4 independent 16-byte loads in flight per thread
+        uint4 u[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) u[j] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(px + j * k) * pitch));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float f[8];
+          unpack8(u[j], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+        }
+      }
+      for (; px < p1; px += k) {
         const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (size_t)px * pitch));
         float f[8];
         unpack8(u, f);
@@ -117,30 +130,44 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
   const int total = (p1 - p0) * nv;
   const int dv = 256 % nv, dp = 256 / nv;
   int v = t % nv, px = p0 + t / nv;
-  for (int e = t; e < total; e += 256) {
-    const int ch = v * 8;
-    const bf16* src = ch < c0 ? x0 + ((size_t)n * hw + px) * pitch0 + ch : x1 + ((size_t)n * hw + px) * pitch1 + (ch - c0);
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
-    float f[8];
-    unpack8(u, f);
-    const float4 a0 = *reinterpret_cast<const float4*>(sa + ch), a1 = *reinterpret_cast<const float4*>(sa + ch + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(sb + ch), b1 = *reinterpret_cast<const float4*>(sb + ch + 4);
-    f[0] = fmaf(f[0], a0.x, b0.x); f[1] = fmaf(f[1], a0.y, b0.y); f[2] = fmaf(f[2], a0.z, b0.z); f[3] = fmaf(f[3], a0.w, b0.w);
-    f[4] = fmaf(f[4], a1.x, b1.x); f[5] = fmaf(f[5], a1.y, b1.y); f[6] = fmaf(f[6], a1.z, b1.z); f[7] = fmaf(f[7], a1.w, b1.w);
-    if (silu) {
+  for (int e = t; e < total; e += 4 * 256) {  // 4 independent 16-byte loads in flight per thread
+    int vv[4], pp[4];
+    uint4 u[4], ad[4];
+    bool ok[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = __fdividef(f[i], 1.f + __expf(-f[i]));
+    for (int j = 0; j < 4; ++j) {
+      vv[j] = v; pp[j] = px; ok[j] = (e + j * 256) < total;
+      if (ok[j]) {
+        const int ch = v * 8;
+        const bf16* src = ch < c0 ? x0 + ((size_t)n * hw + px) * pitch0 + ch : x1 + ((size_t)n * hw + px) * pitch1 + (ch - c0);
+        u[j] = __ldg(reinterpret_cast<const uint4*>(src));
+        if (add != nullptr) ad[j] = __ldg(reinterpret_cast<const uint4*>(add + ((size_t)n * hw + px) * add_pitch + ch));
+      }
+      v += dv; px += dp;
+      if (v >= nv) { v -= nv; ++px; }
     }
-    if (add != nullptr) {
-      const uint4 a = __ldg(reinterpret_cast<const uint4*>(add + ((size_t)n * hw + px) * add_pitch + ch));
-      float g8[8];
-      unpack8(a, g8);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] += g8[i];
+    for (int j = 0; j < 4; ++j) {
+      if (!ok[j]) continue;
+      const int ch = vv[j] * 8;
+      float f[8];
+      unpack8(u[j], f);
+      const float4 a0 = *reinterpret_cast<const float4*>(sa + ch), a1 = *reinterpret_cast<const float4*>(sa + ch + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(sb + ch), b1 = *reinterpret_cast<const float4*>(sb + ch + 4);
+      f[0] = fmaf(f[0], a0.x, b0.x); f[1] = fmaf(f[1], a0.y, b0.y); f[2] = fmaf(f[2], a0.z, b0.z); f[3] = fmaf(f[3], a0.w, b0.w);
+      f[4] = fmaf(f[4], a1.x, b1.x); f[5] = fmaf(f[5], a1.y, b1.y); f[6] = fmaf(f[6], a1.z, b1.z); f[7] = fmaf(f[7], a1.w, b1.w);
+      if (silu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __fdividef(f[i], 1.f + __expf(-f[i]));
+      }
+      if (add != nullptr) {
+        float g8[8];
+        unpack8(ad[j], g8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] += g8[i];
+      }
+      *reinterpret_cast<uint4*>(out + ((size_t)n * hw + pp[j]) * out_pitch + ch) = pack8(f);
     }
-    *reinterpret_cast<uint4*>(out + ((size_t)n * hw + px) * out_pitch + ch) = pack8(f);
-    v += dv; px += dp;
-    if (v >= nv) { v -= nv; ++px; }
   }
 }
 

@@ -83,7 +83,7 @@ for B, heads, nq, nkv in [(16, 5, 3072, 3072), (16, 10, 768, 768), (16, 20, 192,
     C = heads * 64
     q = rnd(B, nq, C); k = rnd(B, nkv, C); v = rnd(B, nkv, C)
     out = torch.empty_like(q)
-    for var in ((0, 1, 2, 4) if nkv > 128 else (0,)):
+    for var in ((0, 1, 4, 5) if nkv > 128 else (0,)):
         t = timeit(lambda: ops.attention(q, k, v, heads, 0.125, out=out, variant=var))
         print(f"  attn B={B} heads={heads} nq={nq} nkv={nkv} variant={var}: {t:7.1f} us  {4 * B * heads * nq * nkv * 64 / t / 1e6:7.1f} TFLOP/s")
 

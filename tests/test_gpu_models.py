@@ -201,3 +201,40 @@ def test_pipeline_pil_output_and_tuple(cuda, small):
                num_inference_steps=2, generator=torch.Generator().manual_seed(7), return_dict=False)
     imgs, nsfw = res
     assert nsfw is None and len(imgs) == 1 and imgs[0].size == (64, 128) and imgs[0].mode == "RGB"  # PIL (W, H), tryon_pipe.py:759-765
+
+
+def test_pipeline_full_size_config0(cuda):
+    """BASELINE.json configs[0]: a single 512x384 pair, 20 DDIM steps, full-size random-init UNet/VAE/EMASC, guidance 7.5 -- the whole
+    `__call__` against the fp32 CPU oracle with identical weights, inputs and noise.  Random weights + CFG 7.5 make the 20-step map
+    chaotic, gate: mean |diff| <= 2/255 (measured 0.55/255, PSNR 51 dB)."""
+    import ctypes
+    try:  # same allocator tuning as bench.py: the fp32 oracle otherwise spends most of its time in page faults
+        libc = ctypes.CDLL("libc.so.6"); libc.mallopt(-3, 1 << 30); libc.mallopt(-1, 1 << 31)
+    except Exception:
+        pass
+    import os
+    from ladi_vton_b200 import synthetic as S
+    from ladi_oracle.parts import DDIMScheduler, EMASC as OE
+    from ladi_oracle.pipeline import OracleTryOnPipeline
+    from ladi_oracle.unet import UNet2DConditionModel as OU
+    from ladi_oracle.vae import AutoencoderKL as OV
+    torch.set_num_threads(min(64, os.cpu_count()))
+    sds = S.build_state_dicts(seed=1234)
+    with torch.device("meta"):
+        ou, ov, oe = OU().eval(), OV().eval(), OE(*sds["emasc_channels"]).eval()
+    ou.load_state_dict(sds["unet"], assign=True); ov.load_state_dict(sds["vae"], assign=True); oe.load_state_dict(sds["emasc"], assign=True)
+    inp = S.synthetic_inputs(1, 512, 384)
+    kw = dict(height=512, width=384, num_inference_steps=20, guidance_scale=7.5)
+    ref = OracleTryOnPipeline(ov, ou, DDIMScheduler(), oe, [1, 2, 3, 4, 5])(
+        inp["image"].clone(), inp["mask_image"].clone(), inp["pose_map"], inp["warped_cloth"], inp["prompt_embeds"],
+        inp["negative_prompt_embeds"], generator=torch.Generator().manual_seed(7), **kw)
+    del ou, ov, oe
+    pipe, _ = S.build_pipeline(cuda, sds=sds)
+    out = pipe(image=inp["image"].clone(), mask_image=inp["mask_image"].clone(), pose_map=inp["pose_map"], warped_cloth=inp["warped_cloth"],
+               prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"],
+               generator=torch.Generator().manual_seed(7), output_type="np", **kw).images
+    mad = float(np.abs(out - ref).mean()) * 255
+    psnr = float(10 * np.log10(1.0 / np.mean((out - ref) ** 2)))
+    print(f"full-size config0 (1x512x384, 20 steps, CFG 7.5): mean|engine-oracle| = {mad:.3f}/255, PSNR {psnr:.1f} dB")
+    assert out.shape == ref.shape == (1, 512, 384, 3)
+    assert mad < 2.0

@@ -115,12 +115,6 @@ LADI_API int ladi_groupnorm_stats(const void* x0, int c0, int pitch0, const void
 LADI_API int ladi_groupnorm_apply(const void* x0, int c0, int pitch0, const void* x1, int c1, int pitch1, int n, int hw, int groups,
                          const float* ws, const float* gamma, const float* beta, float eps, int silu, const void* add,
                          int add_pitch, void* out, int out_pitch, void* stream);
-/* One-launch GroupNorm for low-resolution tensors: a block keeps G whole groups of one image in shared memory (read once, no
- * workspace).  ladi_groupnorm_fused_smem returns the shared memory it needs (0 = unsupported shape); callers use it when <= 200 KiB. */
-LADI_API int64_t ladi_groupnorm_fused_smem(int c0, int c1, int hw, int groups);
-LADI_API int ladi_groupnorm_fused(const void* x0, int c0, int pitch0, const void* x1, int c1, int pitch1, int n, int hw, int groups,
-                         const float* gamma, const float* beta, float eps, int silu, const void* add, int add_pitch, void* out,
-                         int out_pitch, void* stream);
 /* LayerNorm over the last dim (BasicTransformerBlock.norm1/2/3; inversion adapter LayerNorms). */
 LADI_API int ladi_layernorm(const void* x, int x_pitch, int rows, int c, const float* gamma, const float* beta, float eps, void* out,
                    int out_pitch, void* stream);

@@ -95,89 +95,6 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
   }
 }
 
-// ---- GroupNorm in ONE launch for the low-resolution levels (hw <= ~768): a block owns G whole groups of one image, keeps their
-// [hw][G*cpg] slab in shared memory, so the activation is read once and statistics + normalisation need no second kernel.
-// Deterministic (fixed reduction order).  grid = (groups / G, images).
-__global__ void __launch_bounds__(256) gn_fused_kernel(const bf16* __restrict__ x0, int c0, int pitch0, const bf16* __restrict__ x1, int c1,
-                                                       int pitch1, int hw, int groups, int G, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, float eps, int silu, const bf16* __restrict__ add,
-                                                       int add_pitch, bf16* __restrict__ out, int out_pitch) {
-  ptx::pdl_wait();
-  extern __shared__ __align__(16) uint8_t gsm[];
-  const int n = blockIdx.y, t = threadIdx.x;
-  const int Ctot = c0 + c1, cpg = Ctot / groups;
-  const int C = G * cpg, nv = C >> 3;          // channels / 16-byte vectors owned by this block
-  const int cbeg = blockIdx.x * C;
-  uint4* slab = reinterpret_cast<uint4*>(gsm);                                  // [hw][nv]
-  float* ps = reinterpret_cast<float*>(gsm + (size_t)hw * nv * 16);             // [k][C] partial sums
-  const int lanes_v = nv < 256 ? nv : 256;
-  const int k = 256 / lanes_v;
-  float* pq = ps + (size_t)k * C;
-  float* sa = pq + (size_t)k * C;                                               // [C] scale, [C] shift
-  float* sb = sa + C;
-  __shared__ float smean[GN_MAX_GROUPS], srstd[GN_MAX_GROUPS];
-  // phase 1: slab -> shared memory (coalesced 16-byte loads)
-  for (int e = t; e < hw * nv; e += 256) {
-    const int px = e / nv, v = e - px * nv, ch = cbeg + v * 8;
-    const bf16* src = ch < c0 ? x0 + ((size_t)n * hw + px) * pitch0 + ch : x1 + ((size_t)n * hw + px) * pitch1 + (ch - c0);
-    slab[e] = __ldg(reinterpret_cast<const uint4*>(src));
-  }
-  __syncthreads();
-  // phase 2: per-channel partial sums (thread = fixed vector, strided pixels), then per-group totals in a fixed order
-  if (t < lanes_v * k) {
-    const int tv = t % lanes_v, tp = t / lanes_v;
-    for (int v = tv; v < nv; v += lanes_v) {
-      float s[8], q[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-      for (int px = tp; px < hw; px += k) {
-        float f[8];
-        unpack8(slab[px * nv + v], f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { ps[tp * C + v * 8 + i] = s[i]; pq[tp * C + v * 8 + i] = q[i]; }
-    }
-  }
-  __syncthreads();
-  if (t < G) {
-    float s = 0.f, q = 0.f;
-    for (int l = 0; l < k; ++l)
-      for (int c = t * cpg; c < (t + 1) * cpg; ++c) { s += ps[l * C + c]; q += pq[l * C + c]; }
-    const float cnt = (float)hw * (float)cpg;
-    const float mean = s / cnt;
-    smean[t] = mean;
-    srstd[t] = rsqrtf(fmaxf(q / cnt - mean * mean, 0.f) + eps);
-  }
-  __syncthreads();
-  for (int c = t; c < C; c += 256) {
-    const int g = c / cpg;
-    const float a = srstd[g] * __ldg(gamma + cbeg + c);
-    sa[c] = a;
-    sb[c] = __ldg(beta + cbeg + c) - smean[g] * a;
-  }
-  __syncthreads();
-  // phase 3: normalise from shared memory, write coalesced
-  for (int e = t; e < hw * nv; e += 256) {
-    const int px = e / nv, v = e - px * nv, c = v * 8;
-    float f[8];
-    unpack8(slab[e], f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      f[i] = fmaf(f[i], sa[c + i], sb[c + i]);
-      if (silu) f[i] = __fdividef(f[i], 1.f + __expf(-f[i]));
-    }
-    if (add != nullptr) {
-      float g8[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(add + ((size_t)n * hw + px) * add_pitch + cbeg + c)), g8);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] += g8[i];
-    }
-    *reinterpret_cast<uint4*>(out + ((size_t)n * hw + px) * out_pitch + cbeg + c) = pack8(f);
-  }
-}
-
 // ---- GroupNorm pass 2: normalise + affine (+SiLU) (+add), writes the concatenated tensor.  Per-channel scale/shift
 // (rstd*gamma, beta - mean*rstd*gamma) are tabulated once per block in shared memory, so the streaming loop is one FMA (+SiLU)
 // per element with no integer division; the (pixel, vector) walk advances incrementally.
@@ -584,44 +501,6 @@ extern "C" int ladi_groupnorm_apply(const void* x0, int c0, int pitch0, const vo
   LADI_CUDA(ladi_launch(gn_apply_kernel, dim3(dim3(blocks, n)), dim3(256), 0, STREAM, (const bf16*)x0, c0, pitch0, (const bf16*)x1, c1, pitch1, hw, groups, chunks, ws,
                                                        gamma, beta, eps, silu, (const bf16*)add, add_pitch, (bf16*)out, out_pitch, ppb));
   return LADI_OK;
-}
-
-extern "C" int ladi_groupnorm_fused(const void* x0, int c0, int pitch0, const void* x1, int c1, int pitch1, int n, int hw, int groups,
-                                    const float* gamma, const float* beta, float eps, int silu, const void* add, int add_pitch, void* out,
-                                    int out_pitch, void* stream) {
-  if (int e = gn_check(x0, c0, pitch0, x1, c1, pitch1, groups)) return e;
-  LADI_CHECK(out_pitch % 8 == 0 && out_pitch >= c0 + c1, "groupnorm out pitch invalid");
-  const int C = c0 + c1, cpg = C / groups;
-  // smallest G (whole groups per block) whose channel span is a whole number of 16-byte vectors
-  int G = 0;
-  for (int g = 1; g <= groups; g *= 2)
-    if (groups % g == 0 && (g * cpg) % 8 == 0) { G = g; break; }  // a span may cover both sources: each 16-byte vector picks its own
-  LADI_CHECK(G != 0, "groupnorm_fused: no group blocking with 16-byte aligned channel spans (C=%d groups=%d)", C, groups);
-  const int Cb = G * cpg, nv = Cb / 8;
-  const int lanes_v = nv < 256 ? nv : 256, k = 256 / lanes_v;
-  const size_t smem = (size_t)hw * nv * 16 + (size_t)(2 * k * Cb + 2 * Cb) * sizeof(float);
-  LADI_CHECK(smem <= 200 * 1024, "groupnorm_fused: slab of %zu bytes does not fit shared memory (use the two-pass kernels)", smem);
-  static bool attr_set = false;
-  if (!attr_set) {
-    LADI_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
-  LADI_CUDA(ladi_launch(gn_fused_kernel, dim3(groups / G, n), dim3(256), smem, STREAM, (const bf16*)x0, c0, pitch0, (const bf16*)x1, c1, pitch1,
-                        hw, groups, G, gamma, beta, eps, silu, (const bf16*)add, add_pitch, (bf16*)out, out_pitch));
-  return LADI_OK;
-}
-
-/* bytes of shared memory ladi_groupnorm_fused would need (0 = shape not supported): lets the caller choose between the paths */
-extern "C" int64_t ladi_groupnorm_fused_smem(int c0, int c1, int hw, int groups) {
-  const int C = c0 + c1;
-  if (groups <= 0 || C % groups != 0) return 0;
-  const int cpg = C / groups;
-  for (int g = 1; g <= groups; g *= 2)
-    if (groups % g == 0 && (g * cpg) % 8 == 0) {
-      const int Cb = g * cpg, nv = Cb / 8, lanes_v = nv < 256 ? nv : 256, k = 256 / lanes_v;
-      return (int64_t)hw * nv * 16 + (int64_t)(2 * k * Cb + 2 * Cb) * 4;
-    }
-  return 0;
 }
 
 extern "C" int ladi_layernorm(const void* x, int x_pitch, int rows, int c, const float* gamma, const float* beta, float eps, void* out,

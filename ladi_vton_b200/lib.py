@@ -45,8 +45,6 @@ SIGNATURES = {
     "ladi_groupnorm_chunks": ([_I], _I),
     "ladi_groupnorm_stats": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P], _I),
     "ladi_groupnorm_apply": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _F, _I, _P, _I, _P, _I, _P], _I),
-    "ladi_groupnorm_fused_smem": ([_I, _I, _I, _I], _L),
-    "ladi_groupnorm_fused": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _F, _I, _P, _I, _P, _I, _P], _I),
     "ladi_layernorm": ([_P, _I, _I, _I, _P, _P, _F, _P, _I, _P], _I),
     "ladi_softmax_rows": ([_P, _I, _I, _I, _F, _P, _I, _P], _I),
     "ladi_cls_attention": ([_P, _I, _P, _I, _I, _I, _I, _I, _F, _P, _I, _P], _I),

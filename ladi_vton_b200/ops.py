@@ -13,9 +13,6 @@ from .lib import AttnDesc, ConvDesc
 
 ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_GELU = 0, 1, 2, 3
 BK = 64
-FUSED_GROUPNORM = True       # one-launch GroupNorm for low-resolution tensors (slab in shared memory)
-FUSED_GN_SMEM_LIMIT = 200 * 1024
-FUSED_GN_MAX_HW = 768
 PROFILE = None  # bench.py: set to a list to bracket every launch with CUDA events -> (name, start, end, algorithmic flops)
 
 
@@ -180,13 +177,8 @@ def groupnorm(srcs, gamma, beta, groups, eps, ws, silu=False, add=None, out=None
         x1, c1, p1 = None, 0, 0
     if out is None:
         out = torch.empty((n, h, w, c0 + c1), dtype=torch.bfloat16, device=x0.device)
-    s = _stream()
-    need = lib.load().ladi_groupnorm_fused_smem(c0, c1, h * w, groups)
-    if FUSED_GROUPNORM and 0 < need <= FUSED_GN_SMEM_LIMIT and h * w <= FUSED_GN_MAX_HW:
-        _call("ladi_groupnorm_fused", 6.0 * n * h * w * (c0 + c1), _ptr(x0), c0, p0, _ptr(x1), c1, p1, n, h * w, groups, _ptr(gamma),
-              _ptr(beta), eps, int(silu), _ptr(add), (add.stride(2) if add is not None else 0), _ptr(out), out.stride(2), s)
-        return out
     wsb = ws.get(n, h * w, groups)
+    s = _stream()
     _call("ladi_groupnorm_stats", 2.0 * n * h * w * (c0 + c1), _ptr(x0), c0, p0, _ptr(x1), c1, p1, n, h * w, groups, _ptr(wsb), s)
     _call("ladi_groupnorm_apply", 4.0 * n * h * w * (c0 + c1), _ptr(x0), c0, p0, _ptr(x1), c1, p1, n, h * w, groups, _ptr(wsb), _ptr(gamma), _ptr(beta),
              eps, int(silu), _ptr(add), (add.stride(2) if add is not None else 0), _ptr(out), out.stride(2), s)

@@ -249,13 +249,10 @@ def test_attention(cuda, B, heads, nq, nkv, variant):
 
 
 # ------------------------------------------------------------------------------------------------ norms & glue
-@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("n,hw,c0,c1,groups,silu", [(2, 3072, 320, 0, 32, True), (2, 768, 1280, 640, 32, True), (3, 48, 2560, 0, 32, False),
-                                                    (2, 196608, 128, 0, 32, True), (2, 192, 64, 64, 32, True), (2, 768, 640, 0, 32, True),
-                                                    (3, 192, 1280, 1280, 32, True), (2, 48, 1280, 0, 32, True)])
-def test_groupnorm(cuda, n, hw, c0, c1, groups, silu, fused):
+                                                    (2, 196608, 128, 0, 32, True), (2, 192, 64, 64, 32, True)])
+def test_groupnorm(cuda, n, hw, c0, c1, groups, silu):
     from ladi_vton_b200 import ops
-    ops.FUSED_GROUPNORM = fused
     h, w = (hw // 48, 48) if hw % 48 == 0 else (hw, 1)
     x0 = (rnd((n, h, w, c0), cuda, 1) * 2 + 0.5).bfloat16()
     srcs = [x0]
@@ -271,7 +268,6 @@ def test_groupnorm(cuda, n, hw, c0, c1, groups, silu, fused):
         ref = F.silu(ref)
     ref = ref.permute(0, 2, 3, 1)
     torch.cuda.synchronize()
-    ops.FUSED_GROUPNORM = True
     assert nerr(y, ref) < TOL_BF16
 
 

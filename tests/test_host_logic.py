@@ -17,7 +17,7 @@ def test_library_exports_every_declared_symbol():
     from ladi_vton_b200 import lib
     hdr = open(os.path.join(ROOT, "include", "ladi_b200.h")).read()
     declared = set(re.findall(r"LADI_API\s+[\w\s\*]+?\b(ladi_\w+)\s*\(", hdr))
-    assert len(declared) >= 21
+    assert len(declared) >= 19
     assert declared == set(lib.SIGNATURES), declared ^ set(lib.SIGNATURES)
     l = lib.load()  # raises if the .so is missing; getattr raises on a missing export
     for name in declared:

@@ -159,6 +159,27 @@ LADI_API int ladi_ddim_cfg_step(const float* eps, int eps_pitch, float* latents,
 /* (x/2+0.5).clamp(0,1) NHWC bf16/fp32 [n,h,w,pitch] (first 3 channels) -> NHWC fp32 [n,h,w,3] (tryon_pipe.py:356-358). */
 LADI_API int ladi_image_out(const void* x, int x_is_fp32, int n, int h, int w, int x_pitch, float* out, void* stream);
 
+/* ---- text / vision conditioning front-end (not on the per-step path) ------------------------------------
+ * Exact softmax attention for short sequences and any head width that is a multiple of 8 (<= 128), optional causal mask:
+ * the CLIP text transformer driven by src/utils/encode_text_word_embedding.py:41-54 (77 causal tokens, 16 x 64) and the CLIP ViT-H
+ * vision tower called at src/inference.py:269-273 (257 tokens, 16 x 80).  q/k/v/out: bf16 [batch, n, heads*head_dim] views with
+ * row pitches and batch strides in elements (multiples of 8).  nkv <= 1024; causal needs nq == nkv. */
+LADI_API int ladi_attention_small(const void* q, const void* k, const void* v, void* out, int batch, int heads, int nq, int nkv,
+                         int head_dim, int q_pitch, int k_pitch, int v_pitch, int out_pitch, long long q_batch_stride,
+                         long long k_batch_stride, long long v_batch_stride, long long out_batch_stride, float scale, int causal,
+                         void* stream);
+/* out[row,:] = (src[row] >= 0 ? tok[src[row],:] : word_emb[-src[row]-1,:]) + pos[row % seq,:]  (bf16 tables, fp32 sum):
+ * token_embedding + the '$' -> pseudo-word-embedding substitution + position_embedding of
+ * src/utils/encode_text_word_embedding.py:27-38 (the index list `src` is built on the host from input_ids). */
+LADI_API int ladi_clip_embed(const int* src, const void* tok, const void* word_emb, const void* pos, void* out, int rows, int seq, int c,
+                    int out_pitch, void* stream);
+/* pixels NCHW fp32 [n,ch,h,w] -> bf16 rows [n*(h/patch)*(w/patch), k_pad], column (c*patch+ky)*patch+kx, zero padding columns:
+ * the im2col of CLIPVisionEmbeddings.patch_embedding (14x14 stride-14 convolution, no bias), followed by one ladi_conv2d_bf16 GEMM. */
+LADI_API int ladi_patchify(const float* pixels, void* out, int n, int ch, int h, int w, int patch, int k_pad, void* stream);
+/* x[b,0,:] = cls + pos[0,:]; x[b,1+i,:] = patch[b*n_patches+i,:] + pos[1+i,:]  (CLIPVisionEmbeddings.forward), all bf16. */
+LADI_API int ladi_vit_assemble(const void* patch, int patch_pitch, const void* cls, const void* pos, void* out, int n, int n_patches, int c,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -283,3 +283,48 @@ def image_out(x):
     out = torch.empty((n, h, w, 3), dtype=torch.float32, device=x.device)
     lib.call("ladi_image_out", _ptr(x), int(x.dtype == torch.float32), n, h, w, x.stride(2), _ptr(out), _stream())
     return out
+
+
+# ---- text / vision conditioning front-end ---------------------------------------------------------------
+def attention_small(q, k, v, heads, scale, causal=False):
+    """q [B, Nq, heads*hd], k/v [B, Nkv, heads*hd] bf16 views (last dim contiguous) -> [B, Nq, heads*hd] bf16.  Exact softmax,
+    fp32 scores; any head width that is a multiple of 8 (the CLIP ViT-H heads are 80 wide), Nkv <= 1024, optional causal mask."""
+    B, nq, C = q.shape
+    nkv = k.shape[1]
+    hd = C // heads
+    for t in (q, k, v):
+        assert t.dtype == torch.bfloat16 and t.stride(2) == 1
+    out = torch.empty((B, nq, C), dtype=torch.bfloat16, device=q.device)
+    _call("ladi_attention_small", 4.0 * B * heads * nq * nkv * hd, _ptr(q), _ptr(k), _ptr(v), _ptr(out), B, heads, nq, nkv, hd,
+          q.stride(1), k.stride(1), v.stride(1), out.stride(1), q.stride(0), k.stride(0), v.stride(0), out.stride(0), float(scale),
+          1 if causal else 0, _stream(), tag=f"B={B} heads={heads} nq={nq} nkv={nkv} hd={hd}")
+    return out
+
+
+def clip_embed(src, tok, word_emb, pos, seq):
+    """src int32 [rows] (>= 0: token id; < 0: -(row of word_emb) - 1), tok [V, C], word_emb [R, C] or None, pos [seq, C] bf16."""
+    rows, c = src.numel(), tok.shape[1]
+    assert src.dtype == torch.int32 and tok.dtype == torch.bfloat16 and pos.dtype == torch.bfloat16 and tok.is_contiguous() and pos.is_contiguous()
+    assert word_emb is None or (word_emb.dtype == torch.bfloat16 and word_emb.is_contiguous() and word_emb.shape[-1] == c)
+    out = torch.empty((rows, c), dtype=torch.bfloat16, device=tok.device)
+    _call("ladi_clip_embed", 0.0, _ptr(src), _ptr(tok), _ptr(word_emb), _ptr(pos), _ptr(out), rows, seq, c, c, _stream())
+    return out
+
+
+def patchify(pixels, patch, k_pad):
+    """pixels NCHW fp32 -> bf16 [n * gh * gw, k_pad] im2col rows of a patch x patch / stride patch convolution."""
+    n, ch, h, w = pixels.shape
+    assert pixels.dtype == torch.float32 and pixels.is_contiguous()
+    out = torch.empty((n * (h // patch) * (w // patch), k_pad), dtype=torch.bfloat16, device=pixels.device)
+    _call("ladi_patchify", 0.0, _ptr(pixels), _ptr(out), n, ch, h, w, patch, k_pad, _stream())
+    return out
+
+
+def vit_assemble(patch, cls, pos, n):
+    """patch [n * np, C] bf16, cls [C], pos [np + 1, C] -> tokens [n, np + 1, C] bf16."""
+    c = patch.shape[1]
+    np_ = patch.shape[0] // n
+    assert patch.dtype == torch.bfloat16 and patch.stride(1) == 1 and cls.is_contiguous() and pos.is_contiguous()
+    out = torch.empty((n, np_ + 1, c), dtype=torch.bfloat16, device=patch.device)
+    _call("ladi_vit_assemble", 0.0, _ptr(patch), patch.stride(0), _ptr(cls), _ptr(pos), _ptr(out), n, np_, c, _stream())
+    return out

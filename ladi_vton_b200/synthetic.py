@@ -36,7 +36,7 @@ def random_state_dict(shapes, seed, device="cpu", fast=False):
     for k, shp in shapes.items():
         base = k.rsplit(".", 1)[0]
         leaf = base.rsplit(".", 1)[-1]
-        is_norm = leaf.startswith("norm") or leaf in ("group_norm", "conv_norm_out", "layer_norm1", "layer_norm2", "post_layernorm")
+        is_norm = leaf.startswith("norm") or leaf in ("group_norm", "conv_norm_out", "layer_norm1", "layer_norm2", "post_layernorm", "final_layer_norm", "pre_layrnorm")
         if is_norm:
             sd[k] = torch.ones(shp, device=device) if k.endswith("weight") else torch.zeros(shp, device=device)
             continue

@@ -160,3 +160,23 @@ def test_sharding_and_gather_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True, (0, 3)), (1, True, (3, 5))]
+
+
+def test_hub_constructors(tmp_path):
+    """hubconf.py:16-66 names and roles; checkpoints come from local files (no network), missing ones fail loudly."""
+    import torch
+    from ladi_vton_b200 import hub, synthetic as S
+    from ladi_vton_b200.vae import EMASC
+    with pytest.raises(ValueError):
+        hub.extended_unet("viton")
+    with pytest.raises(FileNotFoundError, match="unet_vitonhd.pth"):
+        hub.extended_unet("vitonhd", checkpoint_dir=str(tmp_path))
+    with pytest.raises(NotImplementedError):
+        hub.warping_module("dresscode")
+    ein, eout = [128, 128, 128, 256, 512], [128, 256, 512, 512, 512]
+    sd = S.random_state_dict(S.emasc_param_shapes(ein, eout), 3)
+    torch.save(sd, tmp_path / "emasc_dresscode.pth")
+    m = hub.emasc("dresscode", checkpoint_dir=str(tmp_path))
+    assert isinstance(m, EMASC) and sum(v.numel() for v in sd.values()) == 7_965_696
+    with pytest.raises(RuntimeError):  # wrong key set -> strict load fails like torch's load_state_dict
+        hub.inversion_adapter("vitonhd", state_dict=sd)

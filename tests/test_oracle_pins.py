@@ -134,3 +134,58 @@ def test_mask_features_chained_equals_direct():
     for o, f in zip(out, (1, 1, 2, 4, 8)):
         assert torch.equal(o, 1 - F.interpolate(m, size=(64 // f, 48 // f)))
         assert torch.equal(o[:, 0], 1 - m[:, 0, ::f, ::f])
+
+
+# ---- conditioning front-end: oracle/ladi_oracle/clip.py -------------------------------------------------
+def test_clip_oracle_matches_transformers():
+    """Layer arithmetic + state-dict keys of the restated CLIP towers == the installed transformers classes (shared random weights)."""
+    tr = pytest.importorskip("transformers")
+    from ladi_oracle import clip as oc
+    torch.manual_seed(0)
+    cfg = tr.CLIPTextConfig(hidden_size=64, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2, vocab_size=1000,
+                            max_position_embeddings=77, hidden_act="gelu", eos_token_id=999, bos_token_id=998, pad_token_id=0)
+    hf = tr.CLIPTextModel(cfg).eval()
+    o = oc.ClipTextEncoder(vocab=1000, dim=64, heads=2, layers=2, mlp=256, max_pos=77).eval()
+    o.load_state_dict(hf.state_dict(), strict=True)
+    ids = torch.randint(1, 900, (3, 77))
+    ids[:, 20] = 999
+    with torch.no_grad():
+        a, b = hf(input_ids=ids), o(ids)
+    assert (a.last_hidden_state - b.last_hidden_state).abs().max() < 1e-4
+    assert (a.pooler_output - b.pooler_output).abs().max() < 1e-4
+    vc = tr.CLIPVisionConfig(hidden_size=80, intermediate_size=320, num_hidden_layers=2, num_attention_heads=2, image_size=56, patch_size=14,
+                             hidden_act="gelu")
+    hv = tr.CLIPVisionModel(vc).eval()
+    ov = oc.ClipVisionEncoder(dim=80, heads=2, layers=2, mlp=320, image=56, patch=14).eval()
+    ov.load_state_dict(hv.state_dict(), strict=True)
+    px = torch.randn(2, 3, 56, 56)
+    with torch.no_grad():
+        a, b = hv(pixel_values=px), ov(px)
+    assert (a.last_hidden_state - b.last_hidden_state).abs().max() < 1e-4
+    assert (a.pooler_output - b.pooler_output).abs().max() < 1e-4
+
+
+def test_clip_text_golden_and_engine_key_contract():
+    """tests/golden/clip_text_small.npz was produced by the reference's own encode_text_word_embedding.py running on the oracle text
+    encoder (tests/golden/make_golden_clip.py); the restated function must reproduce it, and the engine's CLIP classes must accept
+    exactly the oracle's (= transformers') state-dict keys and shapes."""
+    import importlib.util
+    from ladi_oracle import clip as oc
+    spec = importlib.util.spec_from_file_location("make_golden_clip", os.path.join(os.path.dirname(GOLD), "make_golden_clip.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    gold = np.load(os.path.join(os.path.dirname(GOLD), "clip_text_small.npz"))
+    enc, ids, we = mg.build()
+    assert np.array_equal(ids.numpy(), gold["input_ids"]) and np.allclose(we.numpy(), gold["word_embeddings"])
+    with torch.no_grad():
+        out = oc.encode_text_word_embedding(enc, ids, we, 4)
+    assert np.abs(out.last_hidden_state.numpy() - gold["last_hidden_state"]).max() < 1e-4
+    assert np.abs(out.pooler_output.numpy() - gold["pooler_output"]).max() < 1e-4
+    from ladi_vton_b200.clip import CLIPTextModel, CLIPVisionModelWithProjection
+    with torch.device("meta"):
+        ot = oc.ClipTextEncoder()
+        ovis = oc.ClipVisionEncoder()
+    assert {k: tuple(v.shape) for k, v in ot.state_dict().items()} == {k: tuple(v) for k, v in CLIPTextModel().param_shapes().items()}
+    assert {k: tuple(v.shape) for k, v in ovis.state_dict().items()} == {k: tuple(v) for k, v in CLIPVisionModelWithProjection().param_shapes().items()}
+    assert sum(p.numel() for p in ot.parameters()) == 340_387_840   # SD-2 text encoder (OpenCLIP ViT-H text tower, 23 layers kept)
+    assert sum(p.numel() for p in ovis.parameters()) == 630_766_080  # CLIP ViT-H/14 vision tower without the projection

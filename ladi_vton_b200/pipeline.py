@@ -275,10 +275,11 @@ class StableDiffusionTryOnePipeline:
         for i in range(num_inference_steps):
             if cloth_input_type == "warped" and i >= n_zero_from and cloth_steps > 0:
                 s.unet_in[..., c_cloth:c_cloth + 4].zero_()
-            if not use_graph or i == 0:
-                self._step(s, cfg, guidance_scale)  # step 0 runs eagerly (also the warm-up before capture)
+            stale = s.graph is None or s.guidance != guidance_scale or s.graph_key != self._graph_key() + (s.coef.data_ptr(),)
+            if not use_graph or (i == 0 and stale):
+                self._step(s, cfg, guidance_scale)  # first step of a new shape runs eagerly: the warm-up before capture
             else:
-                if s.graph is None or s.guidance != guidance_scale or s.graph_key != self._graph_key() + (s.coef.data_ptr(),):
+                if stale:
                     s.graph = torch.cuda.CUDAGraph()
                     n0 = lib.launches
                     with torch.cuda.graph(s.graph):

@@ -36,6 +36,7 @@ extern "C" {
 #define LADI_ACT_SILU 1
 #define LADI_ACT_GEGLU 2
 #define LADI_ACT_GELU 3 /* GELU(erf): CLIP encoder-layer MLP and the adapter's projection MLP (inversion_adapter.py:12-20) */
+#define LADI_ACT_RELU 4 /* warping module: ConvNet_TPS.py:32-42,93-105, unet_parts.py:15-22 */
 
 LADI_API const char* ladi_last_error(void);
 LADI_API int ladi_abi_version(void);
@@ -179,6 +180,34 @@ LADI_API int ladi_patchify(const float* pixels, void* out, int n, int ch, int h,
 /* x[b,0,:] = cls + pos[0,:]; x[b,1+i,:] = patch[b*n_patches+i,:] + pos[1+i,:]  (CLIPVisionEmbeddings.forward), all bf16. */
 LADI_API int ladi_vit_assemble(const void* patch, int patch_pitch, const void* cls, const void* pos, void* out, int n, int n_patches, int c,
                       void* stream);
+
+/* ---- cloth-warping front-end: ConvNet_TPS + refinement U-Net, src/inference.py:236-266 -----------------
+ * torchvision resize(x, (oh, ow), BILINEAR, antialias=True) of an NCHW fp32 tensor, written as channels [c_off, c_off+c) of an NHWC
+ * bf16 tensor (inference.py:239-247: cloth / im_mask / pose_map -> 256x192; the agnostic concat is built in place). */
+LADI_API int ladi_resize_aa(const float* x, int n, int c, int h, int w, int oh, int ow, void* out, int out_pitch, int c_off, void* stream);
+/* NHWC bf16 [n,h,w,c] -> [n,h/2,w/2,4c], channel (sy*2+sx)*c+ch <- pixel (2y+sy, 2x+sx): the 4x4 stride-2 pad-1 convolutions of
+ * FeatureExtraction / FeatureRegression (ConvNet_TPS.py:31-38,93-97) become 3x3 stride-1 pad-1 ladi_conv2d_bf16 calls. */
+LADI_API int ladi_space_to_depth2(const void* x, int n, int h, int w, int c, int x_pitch, void* out, int out_pitch, void* stream);
+/* in place x[row,c] = x[row,c]*scale[c] + shift[c]: eval-mode BatchNorm2d that follows a ReLU (ConvNet_TPS.py:33,39,41). */
+LADI_API int ladi_channel_affine(void* x, long long rows, int c, int pitch, const float* scale, const float* shift, void* stream);
+/* FeatureL2Norm (ConvNet_TPS.py:58-66), in place over the channel dimension of NHWC bf16 rows. */
+LADI_API int ladi_l2norm_channels(void* x, long long rows, int c, int pitch, void* stream);
+/* FeatureCorrelation (ConvNet_TPS.py:69-81): out NHWC bf16 [n,h,w,h*w], out[b,yB,xB,xA*h+yA] = <B[b,yB,xB,:], A[b,yA,xA,:]>. */
+LADI_API int ladi_feature_correlation(const void* feat_a, const void* feat_b, int n, int h, int w, int c, void* out, int out_pitch, void* stream);
+/* points = tanh(theta) (ConvNet_TPS.py:122); grid = target_coordinate_repr @ (inverse_kernel @ [points; 0]) (TPSGridGen.forward,
+ * :183-193).  theta fp32 [n, >= 2*n_ctrl]; inverse_kernel [(n_ctrl+3)^2]; target_coordinate_repr [n_points, n_ctrl+3];
+ * points fp32 [n, n_ctrl, 2]; grid fp32 [n, n_points, 2]. */
+LADI_API int ladi_tps_grid(const float* theta, int theta_pitch, const float* inverse_kernel, const float* target_coordinate_repr, int n, int n_ctrl,
+                  int n_points, float* points, float* grid, void* stream);
+/* inference.py:252-257: antialiased-bilinear resize of low_grid fp32 [n,gh,gw,2] to (h,w) fused with F.grid_sample(cloth, grid,
+ * bilinear, padding_mode='border', align_corners=False); cloth NCHW fp32 [n,c,h,w] -> channels [c_off,c_off+c) of NHWC bf16 out. */
+LADI_API int ladi_warp_grid_sample(const float* low_grid, int gh, int gw, const float* cloth, int n, int c, int h, int w, void* out, int out_pitch,
+                          int c_off, void* stream);
+/* nn.MaxPool2d(2) / nn.Upsample(scale_factor=2, bilinear, align_corners=True) on NHWC bf16 (unet_parts.py:31-34,47). */
+LADI_API int ladi_maxpool2_nhwc(const void* x, int n, int h, int w, int c, void* out, void* stream);
+LADI_API int ladi_upsample2x_bilinear_ac(const void* x, int n, int h, int w, int c, void* out, void* stream);
+/* NHWC fp32 [n,h,w,pitch] (first c channels) -> NCHW fp32 clamped to [lo,hi] (inference.py:262 warped_cloth.clamp(-1,1)). */
+LADI_API int ladi_nhwc_f32_to_nchw_clamp(const float* x, int n, int c, int h, int w, int x_pitch, float lo, float hi, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -326,6 +326,9 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
             } else if (p.act == 3) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            } else if (p.act == 4) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {                            // 4 pieces of 8 columns (16 bytes of bf16)
@@ -412,6 +415,9 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
           } else if (p.act == 3) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+          } else if (p.act == 4) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
           if (p.residual != nullptr) {
             const bf16* rrow = p.residual + grow * p.residual_pitch + col0;
@@ -480,6 +486,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
     }
     if (act == 1) { acc.x = silu_f(acc.x); acc.y = silu_f(acc.y); acc.z = silu_f(acc.z); acc.w = silu_f(acc.w); }
     if (act == 3) { acc.x = gelu_erf(acc.x); acc.y = gelu_erf(acc.y); acc.z = gelu_erf(acc.z); acc.w = gelu_erf(acc.w); }
+    if (act == 4) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
     if (residual != nullptr) {
       const uint2 u = __ldg(reinterpret_cast<const uint2*>(residual + row * residual_pitch + col));
       acc.x += ptx::bf16_lo(u.x); acc.y += ptx::bf16_hi(u.x); acc.z += ptx::bf16_lo(u.y); acc.w += ptx::bf16_hi(u.y);
@@ -532,7 +539,7 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
   LADI_CHECK(d->stride == 1 || d->stride == 2, "stride must be 1 or 2 (got %d)", d->stride);
   LADI_CHECK(d->n_src >= 1 && d->n_src <= 2 && d->n_sc >= 0 && d->n_sc <= 2, "bad source counts");
   LADI_CHECK(d->n > 0 && d->h_out > 0 && d->w_out > 0 && d->c_out > 0, "bad output extent");
-  LADI_CHECK(d->act >= 0 && d->act <= 3, "bad act");
+  LADI_CHECK(d->act >= 0 && d->act <= 4, "bad act");
   LADI_CHECK(d->act != 2 || (d->c_out % 2 == 0 && !d->out_fp32 && d->residual == nullptr), "GEGLU needs even c_out, bf16 out");
   LADI_CHECK(d->out != nullptr && d->weight != nullptr, "null out/weight");
 

@@ -61,6 +61,16 @@ SIGNATURES = {
     "ladi_clip_embed": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
     "ladi_patchify": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "ladi_vit_assemble": ([_P, _I, _P, _P, _P, _I, _I, _I, _P], _I),
+    "ladi_resize_aa": ([_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P], _I),
+    "ladi_space_to_depth2": ([_P, _I, _I, _I, _I, _I, _P, _I, _P], _I),
+    "ladi_channel_affine": ([_P, _L, _I, _I, _P, _P, _P], _I),
+    "ladi_l2norm_channels": ([_P, _L, _I, _I, _P], _I),
+    "ladi_feature_correlation": ([_P, _P, _I, _I, _I, _I, _P, _I, _P], _I),
+    "ladi_tps_grid": ([_P, _I, _P, _P, _I, _I, _I, _P, _P, _P], _I),
+    "ladi_warp_grid_sample": ([_P, _I, _I, _P, _I, _I, _I, _I, _P, _I, _I, _P], _I),
+    "ladi_maxpool2_nhwc": ([_P, _I, _I, _I, _I, _P, _P], _I),
+    "ladi_upsample2x_bilinear_ac": ([_P, _I, _I, _I, _I, _P, _P], _I),
+    "ladi_nhwc_f32_to_nchw_clamp": ([_P, _I, _I, _I, _I, _I, _F, _F, _P, _P], _I),
 }
 
 _lib = None

@@ -11,7 +11,7 @@ import torch
 from . import lib
 from .lib import AttnDesc, ConvDesc
 
-ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_GELU = 0, 1, 2, 3
+ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_GELU, ACT_RELU = 0, 1, 2, 3, 4
 BK = 64
 PROFILE = None  # bench.py: set to a list to bracket every launch with CUDA events -> (name, start, end, algorithmic flops)
 
@@ -327,4 +327,92 @@ def vit_assemble(patch, cls, pos, n):
     assert patch.dtype == torch.bfloat16 and patch.stride(1) == 1 and cls.is_contiguous() and pos.is_contiguous()
     out = torch.empty((n, np_ + 1, c), dtype=torch.bfloat16, device=patch.device)
     _call("ladi_vit_assemble", 0.0, _ptr(patch), patch.stride(0), _ptr(cls), _ptr(pos), _ptr(out), n, np_, c, _stream())
+    return out
+
+
+# ---- cloth-warping front-end -----------------------------------------------------------------------------
+def resize_aa(x, oh, ow, out=None, c_off=0):
+    """torchvision resize(x, (oh, ow), BILINEAR, antialias=True): NCHW fp32 -> channels [c_off, c_off+C) of an NHWC bf16 tensor."""
+    n, c, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = torch.zeros((n, oh, ow, (c + 7) // 8 * 8), dtype=torch.bfloat16, device=x.device)
+    assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.shape[:3] == (n, oh, ow)
+    _call("ladi_resize_aa", 0.0, _ptr(x), n, c, h, w, oh, ow, _ptr(out), out.shape[3], c_off, _stream())
+    return out
+
+
+def space_to_depth2(x, c=None):
+    """NHWC bf16 [n,h,w,pitch] (first c channels) -> [n,h/2,w/2,pad8(4c)] with channel (sy*2+sx)*c + ch; returns (tensor, 4c)."""
+    n, h, w, cc, pitch = _nhwc(x)
+    c = cc if c is None else c
+    out = torch.zeros((n, h // 2, w // 2, (4 * c + 7) // 8 * 8), dtype=torch.bfloat16, device=x.device)
+    _call("ladi_space_to_depth2", 0.0, _ptr(x), n, h, w, c, pitch, _ptr(out), out.shape[3], _stream())
+    return out, 4 * c
+
+
+def channel_affine_(x, scale, shift):
+    n, h, w, c, pitch = _nhwc(x)
+    _call("ladi_channel_affine", 0.0, _ptr(x), n * h * w, c, pitch, _ptr(scale), _ptr(shift), _stream())
+    return x
+
+
+def l2norm_channels_(x):
+    n, h, w, c, pitch = _nhwc(x)
+    _call("ladi_l2norm_channels", 0.0, _ptr(x), n * h * w, c, pitch, _stream())
+    return x
+
+
+def feature_correlation(fa, fb):
+    n, h, w, c, pitch = _nhwc(fa)
+    assert pitch == c and fb.shape == fa.shape and fb.is_contiguous() and fa.is_contiguous()
+    hw = h * w
+    out = torch.zeros((n, h, w, (hw + 7) // 8 * 8), dtype=torch.bfloat16, device=fa.device)
+    _call("ladi_feature_correlation", 2.0 * n * hw * hw * c, _ptr(fa), _ptr(fb), n, h, w, c, _ptr(out), out.shape[3], _stream())
+    return out[..., :hw]
+
+
+def tps_grid(theta, inverse_kernel, target_coordinate_repr, n_ctrl):
+    """theta fp32 [n, 2*n_ctrl] (pre-tanh) -> (points fp32 [n, n_ctrl, 2], grid fp32 [n, n_points, 2])."""
+    n = theta.shape[0]
+    npts = target_coordinate_repr.shape[0]
+    assert theta.dtype == torch.float32 and theta.stride(1) == 1 and inverse_kernel.is_contiguous() and target_coordinate_repr.is_contiguous()
+    points = torch.empty((n, n_ctrl, 2), dtype=torch.float32, device=theta.device)
+    grid = torch.empty((n, npts, 2), dtype=torch.float32, device=theta.device)
+    _call("ladi_tps_grid", 0.0, _ptr(theta), theta.stride(0), _ptr(inverse_kernel), _ptr(target_coordinate_repr), n, n_ctrl, npts, _ptr(points),
+          _ptr(grid), _stream())
+    return points, grid
+
+
+def warp_grid_sample(low_grid, cloth, out, c_off=0):
+    """low_grid fp32 [n,gh,gw,2]; cloth NCHW fp32 [n,c,H,W]; writes channels [c_off, c_off+c) of `out` NHWC bf16 [n,H,W,pitch]."""
+    n, gh, gw, _ = low_grid.shape
+    _, c, H, W = cloth.shape
+    assert low_grid.dtype == torch.float32 and low_grid.is_contiguous() and cloth.dtype == torch.float32 and cloth.is_contiguous()
+    assert out.dtype == torch.bfloat16 and out.is_contiguous() and out.shape[:3] == (n, H, W)
+    _call("ladi_warp_grid_sample", 0.0, _ptr(low_grid), gh, gw, _ptr(cloth), n, c, H, W, _ptr(out), out.shape[3], c_off, _stream())
+    return out
+
+
+def maxpool2(x):
+    n, h, w, c, pitch = _nhwc(x)
+    assert pitch == c and x.is_contiguous()
+    out = torch.empty((n, h // 2, w // 2, c), dtype=torch.bfloat16, device=x.device)
+    _call("ladi_maxpool2_nhwc", 0.0, _ptr(x), n, h, w, c, _ptr(out), _stream())
+    return out
+
+
+def upsample2x_bilinear_ac(x):
+    n, h, w, c, pitch = _nhwc(x)
+    assert pitch == c and x.is_contiguous()
+    out = torch.empty((n, 2 * h, 2 * w, c), dtype=torch.bfloat16, device=x.device)
+    _call("ladi_upsample2x_bilinear_ac", 0.0, _ptr(x), n, h, w, c, _ptr(out), _stream())
+    return out
+
+
+def nhwc_f32_to_nchw_clamp(x, c, lo, hi):
+    n, h, w, pitch = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    _call("ladi_nhwc_f32_to_nchw_clamp", 0.0, _ptr(x), n, c, h, w, pitch, float(lo), float(hi), _ptr(out), _stream())
     return out

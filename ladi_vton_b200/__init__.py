@@ -12,3 +12,4 @@ from .pipeline import StableDiffusionPipelineOutput, StableDiffusionTryOnePipeli
 from .scheduler import DDIMScheduler  # noqa: F401
 from .unet import UNet2DConditionModel, unet_param_shapes  # noqa: F401
 from .vae import EMASC, AutoencoderKL, vae_param_shapes  # noqa: F401
+from .warp import ConvNet_TPS, UNetVanilla, generate_warped_cloth  # noqa: F401

@@ -14,6 +14,7 @@ import torch
 from .adapter import InversionAdapter
 from .unet import UNet2DConditionModel
 from .vae import EMASC
+from .warp import ConvNet_TPS, UNetVanilla
 
 DATASETS = ("dresscode", "vitonhd")
 RELEASE_URL = "https://github.com/miccunifi/ladi-vton/releases/download/weights/"
@@ -52,7 +53,9 @@ def emasc(dataset, checkpoint_dir=None, state_dict=None):
 
 
 def warping_module(dataset, checkpoint_dir=None, state_dict=None):
-    """hubconf.py:56-66 (ConvNet_TPS + UNetVanilla refinement).  SURVEY.md section 8(f) row 2: produces `warped_cloth`, an INPUT of
-    the try-on path; not part of the hot path and not built -- fail loudly rather than fall back to a library implementation."""
-    raise NotImplementedError("warping_module (TPS + refinement) is outside the try-on hot path (SURVEY.md 8(f)-2) and is not built; "
-                              "produce `warped_cloth` with the reference's warping module and pass it to the pipeline")
+    """hubconf.py:56-66: (ConvNet_TPS(256, 192, 21, 3), UNetVanilla(24, 3, bilinear=True)) from `warping_<dataset>.pth`, a dict with
+    the two state dicts under 'tps' and 'refinement'."""
+    ck = state_dict if state_dict is not None else _checkpoint("warping", dataset, checkpoint_dir)
+    tps = ConvNet_TPS(256, 192, 21, 3).load_state_dict(ck["tps"])
+    refinement = UNetVanilla(n_channels=24, n_classes=3, bilinear=True).load_state_dict(ck["refinement"])
+    return tps, refinement

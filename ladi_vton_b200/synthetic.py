@@ -99,3 +99,55 @@ def build_pipeline(device, unet_cfg=None, vae_cfg=None, seed=1234, sds=None, wei
     pipe = StableDiffusionTryOnePipeline(vae=vae, text_encoder=None, tokenizer=None, unet=unet, scheduler=DDIMScheduler(),
                                          emasc=emasc, emasc_int_layers=[1, 2, 3, 4, 5])
     return pipe.to(device), sds
+
+
+def warp_state_dict(shapes, seed, ctrl_bias=None):
+    """Seeded weights for the warping modules (ConvNet_TPS / UNetVanilla key sets): variance-preserving conv weights
+    (U(+-sqrt(6/fan_in)), the nets are ReLU stacks up to 18 layers deep), BatchNorm affine ~ U(0.5,1.5) / N(0,0.1), running statistics
+    N(0,0.1) / U(0.5,1.5); the TPS regression head starts at the identity lattice (`ctrl_bias` = atanh(control points), as
+    ConvNet_TPS.py:199-203) plus a small random linear part so the predicted warp is not the identity."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, shp in shapes.items():
+        leaf = k.rsplit(".", 1)[-1]
+        if k.startswith("gridGen."):
+            continue
+        if leaf == "num_batches_tracked":
+            sd[k] = torch.zeros((), dtype=torch.long)
+        elif leaf == "running_var":
+            sd[k] = torch.rand(shp, generator=g) + 0.5
+        elif leaf == "running_mean":
+            sd[k] = torch.randn(shp, generator=g) * 0.1
+        elif len(shp) == 1 and leaf == "weight":
+            sd[k] = torch.rand(shp, generator=g) + 0.5
+        elif len(shp) == 1:
+            sd[k] = torch.randn(shp, generator=g) * 0.1
+        elif k.endswith("linear.weight"):
+            sd[k] = torch.randn(shp, generator=g) * (0.5 / math.sqrt(shp[1]))
+        else:
+            bound = math.sqrt(6.0 / math.prod(shp[1:]))
+            sd[k] = torch.empty(shp).uniform_(-bound, bound, generator=g)
+            if k.startswith("outc."):
+                sd[k] *= 0.15  # keep the refinement output mostly inside the [-1, 1] clamp of inference.py:262
+    if ctrl_bias is not None:
+        sd["loc_net.regression.linear.bias"] = ctrl_bias.clone()
+    return sd
+
+
+def warp_inputs(B, H, W, seed=1234, n_pose=18):
+    """Smooth synthetic cloth (low-frequency colour field, so that a sub-pixel difference in the sampling grid is a small difference in
+    the warped image), a 3-channel person mask and Gaussian pose heat-maps as in synthetic_inputs."""
+    g = torch.Generator().manual_seed(seed)
+    ys = torch.linspace(0, 1, H)[None, None, :, None]
+    xs = torch.linspace(0, 1, W)[None, None, None, :]
+    ph = torch.rand((B, 3, 1, 1), generator=g) * 6.28
+    fy = torch.rand((B, 3, 1, 1), generator=g) * 3 + 1
+    fx = torch.rand((B, 3, 1, 1), generator=g) * 3 + 1
+    cloth = torch.sin(6.28 * (fy * ys + fx * xs) + ph) * 0.9
+    im_mask = (torch.rand((B, 3, H, W), generator=g) * 2 - 1) * (ys > 0.3).float()
+    cy = torch.rand((B, n_pose, 1, 1), generator=g) * H
+    cx = torch.rand((B, n_pose, 1, 1), generator=g) * W
+    yy = torch.arange(H, dtype=torch.float32)[None, None, :, None]
+    xx = torch.arange(W, dtype=torch.float32)[None, None, None, :]
+    pose = torch.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / 81.0)
+    return dict(cloth=cloth, im_mask=im_mask, pose_map=pose)

@@ -171,8 +171,8 @@ def test_hub_constructors(tmp_path):
         hub.extended_unet("viton")
     with pytest.raises(FileNotFoundError, match="unet_vitonhd.pth"):
         hub.extended_unet("vitonhd", checkpoint_dir=str(tmp_path))
-    with pytest.raises(NotImplementedError):
-        hub.warping_module("dresscode")
+    with pytest.raises(FileNotFoundError, match="warping_dresscode.pth"):
+        hub.warping_module("dresscode", checkpoint_dir=str(tmp_path))
     ein, eout = [128, 128, 128, 256, 512], [128, 256, 512, 512, 512]
     sd = S.random_state_dict(S.emasc_param_shapes(ein, eout), 3)
     torch.save(sd, tmp_path / "emasc_dresscode.pth")

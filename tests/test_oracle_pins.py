@@ -189,3 +189,60 @@ def test_clip_text_golden_and_engine_key_contract():
     assert {k: tuple(v.shape) for k, v in ovis.state_dict().items()} == {k: tuple(v) for k, v in CLIPVisionModelWithProjection().param_shapes().items()}
     assert sum(p.numel() for p in ot.parameters()) == 340_387_840   # SD-2 text encoder (OpenCLIP ViT-H text tower, 23 layers kept)
     assert sum(p.numel() for p in ovis.parameters()) == 630_766_080  # CLIP ViT-H/14 vision tower without the projection
+
+
+# ---- cloth-warping front-end: oracle/ladi_oracle/warp.py -------------------------------------------------
+def _load_script(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join(os.path.dirname(GOLD), name + ".py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_warp_oracle_reproduces_reference_golden():
+    """tests/golden/warp_small.npz came from the reference's own ConvNet_TPS / UNetVanilla classes (make_golden_warp.py); the restated
+    oracle, fed the same seeded weights and inputs, must reproduce control points, TPS grid, precomputed matrices and U-Net output."""
+    from ladi_oracle import warp as ow
+    mg = _load_script("make_golden_warp")
+    gold = np.load(os.path.join(os.path.dirname(GOLD), "warp_small.npz"))
+    tps_sd, unet_sd = mg.build_weights()
+    tps = ow.ConvNet_TPS(256, 192, 21, 3).eval()
+    missing = tps.load_state_dict(tps_sd, strict=False)
+    assert sorted(missing.missing_keys) == ["gridGen.inverse_kernel", "gridGen.padding_matrix", "gridGen.target_coordinate_repr"]
+    unet = ow.UNetVanilla(24, 3, True).eval()
+    unet.load_state_dict(unet_sd)
+    a, b, x = mg.build_inputs()
+    with torch.no_grad():
+        grid, pts = tps(a, b)
+        y = unet(x)
+    assert np.abs(tps.gridGen.inverse_kernel.numpy() - gold["inverse_kernel"]).max() < 1e-4
+    assert np.abs(tps.gridGen.target_coordinate_repr[::97].numpy() - gold["repr_sub"]).max() < 1e-5
+    assert np.abs(pts.numpy() - gold["points"]).max() < 1e-4
+    assert np.abs(grid[:, ::8, ::8].numpy() - gold["grid_sub"]).max() < 1e-3
+    assert np.abs(y.numpy() - gold["unet_out"]).max() < 1e-3 * max(1.0, float(np.abs(gold["unet_out"]).max()))
+
+
+def test_warp_key_contract_and_counts():
+    from ladi_oracle import warp as ow
+    from ladi_vton_b200.warp import ConvNet_TPS, UNetVanilla
+    o, e = ow.ConvNet_TPS(256, 192, 21, 3), ConvNet_TPS(256, 192, 21, 3)
+    assert {k: tuple(v.shape) for k, v in o.state_dict().items()} == {k: tuple(v) for k, v in e.param_shapes().items()}
+    ou, eu = ow.UNetVanilla(24, 3, True), UNetVanilla(24, 3, True)
+    assert {k: tuple(v.shape) for k, v in ou.state_dict().items()} == {k: tuple(v) for k, v in eu.param_shapes().items()}
+    assert sum(p.numel() for p in o.parameters()) == 19_056_626 and sum(p.numel() for p in ou.parameters()) == 17_275_203
+    with pytest.raises(NotImplementedError):
+        UNetVanilla(24, 3, bilinear=False)
+    with pytest.raises(ValueError):
+        ConvNet_TPS(250, 192, 21, 3)
+
+
+def test_s2d_weight_equals_strided_conv():
+    """The engine computes the 4x4 stride-2 pad-1 convolutions of ConvNet_TPS as 3x3 stride-1 convolutions over a space-to-depth
+    tensor; the weight re-indexing is host logic and is checked here against torch's strided convolution."""
+    import torch.nn.functional as F
+    from ladi_vton_b200.warp import s2d_weight
+    g = torch.Generator().manual_seed(0)
+    x, w = torch.randn((2, 5, 8, 6), generator=g), torch.randn((7, 5, 4, 4), generator=g)
+    xs = x.view(2, 5, 4, 2, 3, 2).permute(0, 3, 5, 1, 2, 4).reshape(2, 20, 4, 3)  # channel (sy*2+sx)*c + ch
+    assert (F.conv2d(x, w, stride=2, padding=1) - F.conv2d(xs, s2d_weight(w), stride=1, padding=1)).abs().max() < 1e-4

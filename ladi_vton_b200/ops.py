@@ -376,7 +376,8 @@ def tps_grid(theta, inverse_kernel, target_coordinate_repr, n_ctrl):
     """theta fp32 [n, 2*n_ctrl] (pre-tanh) -> (points fp32 [n, n_ctrl, 2], grid fp32 [n, n_points, 2])."""
     n = theta.shape[0]
     npts = target_coordinate_repr.shape[0]
-    assert theta.dtype == torch.float32 and theta.stride(1) == 1 and inverse_kernel.is_contiguous() and target_coordinate_repr.is_contiguous()
+    assert theta.dtype == torch.float32 and theta.stride(1) == 1
+    inverse_kernel, target_coordinate_repr = inverse_kernel.contiguous(), target_coordinate_repr.contiguous()  # torch.inverse is column-major
     points = torch.empty((n, n_ctrl, 2), dtype=torch.float32, device=theta.device)
     grid = torch.empty((n, npts, 2), dtype=torch.float32, device=theta.device)
     _call("ladi_tps_grid", 0.0, _ptr(theta), theta.stride(0), _ptr(inverse_kernel), _ptr(target_coordinate_repr), n, n_ctrl, npts, _ptr(points),

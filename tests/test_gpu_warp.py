@@ -3,8 +3,8 @@
 
 Tolerances: data-movement kernels exact; fp32 geometry kernels <= 1e-4 absolute; kernels with bf16 outputs within bf16 rounding of the
 fp32 result (<= 1e-2 relative); assembled networks (bf16 activations, the reference runs them in fp32): control points and TPS grid
-<= 3e-2 absolute in normalised [-1, 1] coordinates, refinement U-Net <= 3e-2 relative L2, refined warped cloth (end to end, smooth
-synthetic cloth) <= 8e-2 relative L2.
+<= 1e-2 absolute in normalised [-1, 1] coordinates (measured 2e-3), refinement U-Net <= 2e-2 relative L2 (measured 6-8e-3), refined
+warped cloth (end to end, smooth synthetic cloth) <= 3e-2 relative L2 (measured 5e-3).
 """
 import pytest
 import torch
@@ -80,7 +80,7 @@ def test_tps_grid_and_sampling(cuda):
     theta = torch.atanh(ctrl).view(1, -1).repeat(3, 1) + torch.randn((3, 50), generator=g) * 0.2
     pts_ref = torch.tanh(theta).view(3, 25, 2)
     grid_ref = gen(pts_ref).view(3, 64, 48, 2)
-    pts, grid = ops.tps_grid(theta.to(cuda), gen.inverse_kernel.to(cuda), gen.target_coordinate_repr.to(cuda).contiguous(), 25)
+    pts, grid = ops.tps_grid(theta.to(cuda), gen.inverse_kernel.to(cuda), gen.target_coordinate_repr.to(cuda), 25)
     assert (pts.cpu() - pts_ref).abs().max() < 1e-5 and (grid.cpu().view(3, 64, 48, 2) - grid_ref).abs().max() < 1e-4
     # inference.py:252-257 with the exact low-resolution grid: resize to (128, 96) + grid_sample(border)
     cloth = S.warp_inputs(3, 128, 96, seed=3)["cloth"]
@@ -143,7 +143,7 @@ def test_convnet_tps(cuda):
     moved = (pts_ref - control_points()).abs().max().item()
     print("TPS control points / grid max abs err:", e_pts, e_grid, "(warp moves the lattice by up to", moved, ")")
     assert moved > 0.05, "test weights must produce a non-identity warp"
-    assert e_pts < 3e-2 and e_grid < 3e-2
+    assert e_pts < 1e-2 and e_grid < 1e-2
 
 
 @pytest.mark.parametrize("widths,hw", [((16, 32, 64, 128, 256), (64, 48)), ((64, 128, 256, 512, 1024), (64, 48))])
@@ -155,7 +155,7 @@ def test_unet_vanilla(cuda, widths, hw):
     y = eng(x)
     err = rel_l2(y, ref)
     print("UNetVanilla rel-L2:", err)
-    assert y.shape == ref.shape and err < 3e-2
+    assert y.shape == ref.shape and err < 2e-2
     with pytest.raises(NotImplementedError):
         eng(torch.zeros((1, 24, 40, 48)))
 
@@ -174,7 +174,7 @@ def test_generate_warped_cloth_full_size(cuda):
     err = rel_l2(got, want)
     sat = float((want.abs() >= 1.0).float().mean())
     print("refined warped cloth rel-L2:", err, "mean |diff|:", float((got.cpu() - want).abs().mean()), "clamped fraction:", sat)
-    assert err < 8e-2
+    assert err < 3e-2
     # stage check with the oracle's own low-resolution grid: the fused grid-resize + grid_sample kernel alone
     x = torch.zeros((1, 512, 384, 8), dtype=torch.bfloat16, device=cuda)
     ops.warp_grid_sample(low_grid.to(cuda).contiguous(), inp["cloth"].to(cuda), x)

@@ -24,6 +24,22 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int GN_MAX_GROUPS = 64;
 constexpr int GN_MAX_CHUNKS = 64;
 
@@ -50,6 +66,9 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
   const int p0 = chunk * per, p1 = min(hw, p0 + per);
   const int lanes_v = nv < 256 ? nv : 256;
   const int k = 256 / lanes_v;
+  // The kernel is instruction-issue bound (ncu: 70 % issue-active, 96 % L2 hits), so the streaming loop is written for few integer
+  // instructions: one base pointer per thread advanced by a constant byte stride, full batches of 8 loads without predicates, one
+  // predicated batch of 4 for the ragged end.
   if (t < lanes_v * k) {
     const int tv = t % lanes_v, tp = t / lanes_v;
     for (int v = tv; v < nv; v += lanes_v) {
@@ -61,57 +80,134 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const bf16* __restrict__ 
       float s[8], q[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-      int px = p0 + tp;
-      for (; px + 3 * k < p1; px += 4 * k) {  // 4 independent 16-byte loads in flight per thread
+      const uint4* ptr = reinterpret_cast<const uint4*>(base + (size_t)(p0 + tp) * pitch);
+      const size_t stride = (size_t)k * pitch / 8;  // in 16-byte units (pitch % 8 == 0)
+      int cnt = p1 - p0 - tp;                       // pixels p0+tp, p0+tp+k, ... < p1
+      cnt = cnt > 0 ? (cnt + k - 1) / k : 0;
+      for (; cnt >= 8; cnt -= 8, ptr += 8 * stride) {
+        uint4 u[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) u[j] = __ldg(ptr + j * stride);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float f[8];
+          unpack8(u[j], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
+        }
+      }
+      for (; cnt > 0; cnt -= 4, ptr += 4 * stride) {
         uint4 u[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) u[j] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(px + j * k) * pitch));
+        for (int j = 0; j < 4; ++j) u[j] = j < cnt ? __ldg(ptr + j * stride) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float f[8];
           unpack8(u[j], f);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+          for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] = fmaf(f[i], f[i], q[i]); }
         }
-      }
-      for (; px < p1; px += k) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + (size_t)px * pitch));
-        float f[8];
-        unpack8(u, f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) { ps[tp * C + v * 8 + i] = s[i]; pq[tp * C + v * 8 + i] = q[i]; }
     }
   }
   __syncthreads();
-  if (t < gps) {
+  // fold the k * cpg per-thread partials of every group with 8 lanes per group: lane `part` takes channels part, part+8, ... of the
+  // group for every pixel lane (no integer division), then a fixed shuffle tree -- deterministic
+  const int part = t & 7;
+  for (int base = 0; base < gps; base += 32) {  // uniform trip count: the shuffles below need whole warps
+    const int gi = base + (t >> 3);
     float s = 0.f, q = 0.f;
-    for (int l = 0; l < k; ++l)
-      for (int c = t * cpg; c < (t + 1) * cpg; ++c) { s += ps[l * C + c]; q += pq[l * C + c]; }
-    float* dst = ws + (((size_t)n * chunks + chunk) * groups + blockIdx.z * gps + t) * 2;
-    dst[0] = s; dst[1] = q;
+    if (gi < gps) {
+      for (int l = 0; l < k; ++l) {
+        const float* rs = ps + l * C + gi * cpg;
+        const float* rq = pq + l * C + gi * cpg;
+        for (int c = part; c < cpg; c += 8) { s += rs[c]; q += rq[c]; }
+      }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (gi < gps && part == 0) {
+      float* dst = ws + (((size_t)n * chunks + chunk) * groups + blockIdx.z * gps + gi) * 2;
+      dst[0] = s; dst[1] = q;
+    }
   }
 }
 
 // ---- GroupNorm pass 2: normalise + affine (+SiLU) (+add), writes the concatenated tensor.  Per-channel scale/shift
 // (rstd*gamma, beta - mean*rstd*gamma) are tabulated once per block in shared memory, so the streaming loop is one FMA (+SiLU)
 // per element with no integer division; the (pixel, vector) walk advances incrementally.
-__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x0, int c0, int pitch0, const bf16* __restrict__ x1,
+template <bool HAS_ADD>
+__global__ void __launch_bounds__(256, 3) gn_apply_kernel(const bf16* __restrict__ x0, int c0, int pitch0, const bf16* __restrict__ x1,
                                                        int c1, int pitch1, int hw, int groups, int chunks, const float* __restrict__ ws,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                        int silu, const bf16* __restrict__ add, int add_pitch, bf16* __restrict__ out,
                                                        int out_pitch, int px_per_block) {
   ptx::pdl_wait();
   __shared__ float smean[GN_MAX_GROUPS], srstd[GN_MAX_GROUPS];
+  __shared__ float reds[8][GN_MAX_GROUPS], redq[8][GN_MAX_GROUPS];
   __shared__ __align__(16) float sa[GN_SLOTS], sb[GN_SLOTS];
   const int n = blockIdx.y, t = threadIdx.x;
   const int C = c0 + c1, nv = C >> 3, cpg = C / groups;
+  // ---- streaming walk: element e = t, t+256, ... of this block's (pixel, vector) range; NB independent 16-byte loads in flight per
+  // thread; the first batch is issued BEFORE the statistics prologue so its latency overlaps the prologue's.  The kernel is
+  // instruction-issue bound (ncu), so addresses are strength-reduced: per-source row pointers advance by constant strides and are
+  // corrected on the (pixel, vector) wrap instead of being recomputed with 64-bit multiplies.
+  constexpr int NB = 8;
+  const int p0 = blockIdx.x * px_per_block, p1 = min(hw, p0 + px_per_block);
+  const int total = (p1 - p0) * nv;
+  const int dv = 256 % nv, dp = 256 / nv;
+  struct Cursor {
+    int v;
+    const bf16 *r0, *r1, *ra;  // row pointers of the current pixel in source 0 / source 1 (pre-offset by -c0) / the add operand
+  };
+  Cursor lc;
+  {
+    const int px = p0 + t / nv;
+    lc.v = t % nv;
+    lc.r0 = x0 + ((size_t)n * hw + px) * pitch0;
+    lc.r1 = c1 > 0 ? x1 + ((size_t)n * hw + px) * pitch1 - c0 : lc.r0;
+    lc.ra = HAS_ADD ? add + ((size_t)n * hw + px) * add_pitch : nullptr;
+  }
+  const int step0 = dp * pitch0, step1 = dp * pitch1, stepa = dp * add_pitch;
+  auto advance = [&](Cursor& c) {
+    c.v += dv; c.r0 += step0; c.r1 += step1;
+    if (HAS_ADD) c.ra += stepa;
+    if (c.v >= nv) {
+      c.v -= nv; c.r0 += pitch0; c.r1 += pitch1;
+      if (HAS_ADD) c.ra += add_pitch;
+    }
+  };
+  uint4 u[NB], ad[HAS_ADD ? NB : 1];
+  auto load_batch = [&](int e) {
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (e + j * 256 < total) {
+        const int ch = lc.v * 8;
+        u[j] = __ldg(reinterpret_cast<const uint4*>((ch < c0 ? lc.r0 : lc.r1) + ch));
+        if (HAS_ADD) ad[HAS_ADD ? j : 0] = __ldg(reinterpret_cast<const uint4*>(lc.ra + ch));
+      }
+      advance(lc);
+    }
+  };
+  load_batch(t);
+  // ---- prologue: fold the per-chunk partials.  `slices` threads per group take interleaved chunks (independent loads in flight), then
+  // one thread per group adds the slices in a fixed order -- deterministic, and ~8x shorter than one thread walking all chunks
+  const int slices = min(8, 256 / groups);
+  {
+    const int g = t % groups, sl = t / groups;
+    if (sl < slices) {
+      float s = 0.f, q = 0.f;
+      const float* src = ws + (size_t)n * chunks * groups * 2 + g * 2;
+      for (int c = sl; c < chunks; c += slices) { s += src[(size_t)c * groups * 2]; q += src[(size_t)c * groups * 2 + 1]; }
+      reds[sl][g] = s; redq[sl][g] = q;
+    }
+  }
+  __syncthreads();
   if (t < groups) {
     float s = 0.f, q = 0.f;
-    const float* src = ws + (size_t)n * chunks * groups * 2 + t * 2;
-    for (int c = 0; c < chunks; ++c) { s += src[(size_t)c * groups * 2]; q += src[(size_t)c * groups * 2 + 1]; }
+    for (int sl = 0; sl < slices; ++sl) { s += reds[sl][t]; q += redq[sl][t]; }
     const float cnt = (float)hw * (float)cpg;
     const float mean = s / cnt;
     const float var = fmaxf(q / cnt - mean * mean, 0.f);
@@ -126,48 +222,39 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ 
     sb[c] = __ldg(beta + c) - smean[g] * a;
   }
   __syncthreads();
-  const int p0 = blockIdx.x * px_per_block, p1 = min(hw, p0 + px_per_block);
-  const int total = (p1 - p0) * nv;
-  const int dv = 256 % nv, dp = 256 / nv;
-  int v = t % nv, px = p0 + t / nv;
-  for (int e = t; e < total; e += 4 * 256) {  // 4 independent 16-byte loads in flight per thread
-    int vv[4], pp[4];
-    uint4 u[4], ad[4];
-    bool ok[4];
+  int v = t % nv;  // process cursor (trails the load cursor by one batch)
+  bf16* orow = out + ((size_t)n * hw + p0 + t / nv) * out_pitch;
+  const int stepo = dp * out_pitch;
+  for (int e = t; e < total; e += NB * 256) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      vv[j] = v; pp[j] = px; ok[j] = (e + j * 256) < total;
-      if (ok[j]) {
+    for (int j = 0; j < NB; ++j) {
+      if (e + j * 256 < total) {
         const int ch = v * 8;
-        const bf16* src = ch < c0 ? x0 + ((size_t)n * hw + px) * pitch0 + ch : x1 + ((size_t)n * hw + px) * pitch1 + (ch - c0);
-        u[j] = __ldg(reinterpret_cast<const uint4*>(src));
-        if (add != nullptr) ad[j] = __ldg(reinterpret_cast<const uint4*>(add + ((size_t)n * hw + px) * add_pitch + ch));
+        float f[8];
+        unpack8(u[j], f);
+        const float4 a0 = *reinterpret_cast<const float4*>(sa + ch), a1 = *reinterpret_cast<const float4*>(sa + ch + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(sb + ch), b1 = *reinterpret_cast<const float4*>(sb + ch + 4);
+        f[0] = fmaf(f[0], a0.x, b0.x); f[1] = fmaf(f[1], a0.y, b0.y); f[2] = fmaf(f[2], a0.z, b0.z); f[3] = fmaf(f[3], a0.w, b0.w);
+        f[4] = fmaf(f[4], a1.x, b1.x); f[5] = fmaf(f[5], a1.y, b1.y); f[6] = fmaf(f[6], a1.z, b1.z); f[7] = fmaf(f[7], a1.w, b1.w);
+        if (silu) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {  // x * sigmoid(x) = h * (1 + tanh(h)), h = x / 2: ONE MUFU (tanh.approx, rel. error 2^-11,
+            const float h = 0.5f * f[i];  // below the bf16 rounding of the result) instead of ex2 + rcp -- the kernel is MUFU/issue bound
+            f[i] = fmaf(h, tanh_approx(h), h);
+          }
+        }
+        if (HAS_ADD) {
+          float g8[8];
+          unpack8(ad[HAS_ADD ? j : 0], g8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] += g8[i];
+        }
+        *reinterpret_cast<uint4*>(orow + ch) = pack8(f);
       }
-      v += dv; px += dp;
-      if (v >= nv) { v -= nv; ++px; }
+      v += dv; orow += stepo;
+      if (v >= nv) { v -= nv; orow += out_pitch; }
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (!ok[j]) continue;
-      const int ch = vv[j] * 8;
-      float f[8];
-      unpack8(u[j], f);
-      const float4 a0 = *reinterpret_cast<const float4*>(sa + ch), a1 = *reinterpret_cast<const float4*>(sa + ch + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(sb + ch), b1 = *reinterpret_cast<const float4*>(sb + ch + 4);
-      f[0] = fmaf(f[0], a0.x, b0.x); f[1] = fmaf(f[1], a0.y, b0.y); f[2] = fmaf(f[2], a0.z, b0.z); f[3] = fmaf(f[3], a0.w, b0.w);
-      f[4] = fmaf(f[4], a1.x, b1.x); f[5] = fmaf(f[5], a1.y, b1.y); f[6] = fmaf(f[6], a1.z, b1.z); f[7] = fmaf(f[7], a1.w, b1.w);
-      if (silu) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = __fdividef(f[i], 1.f + __expf(-f[i]));
-      }
-      if (add != nullptr) {
-        float g8[8];
-        unpack8(ad[j], g8);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] += g8[i];
-      }
-      *reinterpret_cast<uint4*>(out + ((size_t)n * hw + pp[j]) * out_pitch + ch) = pack8(f);
-    }
+    if (e + NB * 256 < total) load_batch(e + NB * 256);
   }
 }
 
@@ -493,13 +580,17 @@ extern "C" int ladi_groupnorm_apply(const void* x0, int c0, int pitch0, const vo
   const int chunks = gn_chunks(hw);
   const int nv = (c0 + c1) / 8;
   int ppb = (256 * 16) / nv;  // >= 16 vectors per thread, and few enough blocks that the per-block channel table amortises
-  const int target_blocks = (ladi_num_sms() * 4 + n - 1) / n;
+  const int target_blocks = (ladi_num_sms() * 3 + n - 1) / n;  // 3 resident blocks per SM (launch bounds): the whole grid is one wave
   const int ppb2 = (hw + target_blocks - 1) / target_blocks;
   if (ppb2 > ppb) ppb = ppb2;
   if (ppb < 1) ppb = 1;
   const int blocks = (hw + ppb - 1) / ppb;
-  LADI_CUDA(ladi_launch(gn_apply_kernel, dim3(dim3(blocks, n)), dim3(256), 0, STREAM, (const bf16*)x0, c0, pitch0, (const bf16*)x1, c1, pitch1, hw, groups, chunks, ws,
-                                                       gamma, beta, eps, silu, (const bf16*)add, add_pitch, (bf16*)out, out_pitch, ppb));
+  if (add != nullptr)
+    LADI_CUDA(ladi_launch(gn_apply_kernel<true>, dim3(dim3(blocks, n)), dim3(256), 0, STREAM, (const bf16*)x0, c0, pitch0, (const bf16*)x1, c1, pitch1, hw, groups, chunks, ws,
+                          gamma, beta, eps, silu, (const bf16*)add, add_pitch, (bf16*)out, out_pitch, ppb));
+  else
+    LADI_CUDA(ladi_launch(gn_apply_kernel<false>, dim3(dim3(blocks, n)), dim3(256), 0, STREAM, (const bf16*)x0, c0, pitch0, (const bf16*)x1, c1, pitch1, hw, groups, chunks, ws,
+                          gamma, beta, eps, silu, (const bf16*)add, add_pitch, (bf16*)out, out_pitch, ppb));
   return LADI_OK;
 }
 

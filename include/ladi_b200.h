@@ -185,6 +185,11 @@ LADI_API int ladi_vit_assemble(const void* patch, int patch_pitch, const void* c
  * torchvision resize(x, (oh, ow), BILINEAR, antialias=True) of an NCHW fp32 tensor, written as channels [c_off, c_off+c) of an NHWC
  * bf16 tensor (inference.py:239-247: cloth / im_mask / pose_map -> 256x192; the agnostic concat is built in place). */
 LADI_API int ladi_resize_aa(const float* x, int n, int c, int h, int w, int oh, int ow, void* out, int out_pitch, int c_off, void* stream);
+/* src/inference.py:265-271: torchvision resize((cloth + 1) / 2, (oh, ow), antialias=True).clamp(0, 1) followed by the CLIP image
+ * processor's per-channel (v - mean) / std (AutoProcessor call, :267): x NCHW fp32 in [-1,1] -> out NCHW fp32 [n,c,oh,ow], the
+ * `pixel_values` of the vision tower.  quantise != 0: v = floor(v * 255) / 255 first (a processor that round-trips through uint8). */
+LADI_API int ladi_clip_preprocess(const float* x, int n, int c, int h, int w, int oh, int ow, const float* mean, const float* stdev,
+                         int quantise, float* out, void* stream);
 /* NHWC bf16 [n,h,w,c] -> [n,h/2,w/2,4c], channel (sy*2+sx)*c+ch <- pixel (2y+sy, 2x+sx): the 4x4 stride-2 pad-1 convolutions of
  * FeatureExtraction / FeatureRegression (ConvNet_TPS.py:31-38,93-97) become 3x3 stride-1 pad-1 ladi_conv2d_bf16 calls. */
 LADI_API int ladi_space_to_depth2(const void* x, int n, int h, int w, int c, int x_pitch, void* out, int out_pitch, void* stream);

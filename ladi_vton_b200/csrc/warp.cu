@@ -39,6 +39,35 @@ __device__ __forceinline__ void aa_taps(int o, int in_size, int out_size, AATaps
   t.count = cnt;
 }
 
+// src/inference.py:265-271: resize((cloth + 1) / 2, (224, 224), antialias=True).clamp(0, 1), then the CLIP image processor's
+// (x - mean) / std, fused: x NCHW fp32 in [-1,1] -> out NCHW fp32 [n,c,oh,ow].  The filter is linear, so the (x+1)/2 affine commutes
+// with it.  `quantise` != 0 reproduces a processor that round-trips the [0,1] floats through uint8 (floor(v * 255) / 255).
+__global__ void __launch_bounds__(256) clip_preprocess_kernel(const float* __restrict__ x, int n, int c, int h, int w, int oh, int ow,
+                                                              const float* __restrict__ mean, const float* __restrict__ stdev,
+                                                              int quantise, float* __restrict__ out) {
+  ptx::pdl_wait();
+  const long long total = (long long)n * oh * ow;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int ox = (int)(i % ow), oy = (int)((i / ow) % oh), b = (int)(i / ((long long)ow * oh));
+    AATaps ty, tx;
+    aa_taps(oy, h, oh, ty);
+    aa_taps(ox, w, ow, tx);
+    for (int ch = 0; ch < c; ++ch) {
+      const float* src = x + ((size_t)b * c + ch) * h * w;
+      float acc = 0.f;
+      for (int a = 0; a < ty.count; ++a) {
+        const float* row = src + (size_t)(ty.first + a) * w + tx.first;
+        float r = 0.f;
+        for (int k = 0; k < tx.count; ++k) r = fmaf(tx.w[k], __ldg(row + k), r);
+        acc = fmaf(ty.w[a], r, acc);
+      }
+      float v = fminf(fmaxf(fmaf(acc, 0.5f, 0.5f), 0.f), 1.f);
+      if (quantise) v = floorf(v * 255.f) * (1.f / 255.f);
+      out[(((size_t)b * c + ch) * oh + oy) * ow + ox] = (v - __ldg(mean + ch)) / __ldg(stdev + ch);
+    }
+  }
+}
+
 // x NCHW fp32 [n,c,h,w] -> out NHWC bf16 [n,oh,ow,pitch] channels [c_off, c_off+c)   (torchvision resize(..., BILINEAR, antialias=True))
 __global__ void __launch_bounds__(256) resize_aa_kernel(const float* __restrict__ x, int n, int c, int h, int w, int oh, int ow,
                                                         bf16* __restrict__ out, int out_pitch, int c_off) {
@@ -314,6 +343,15 @@ inline int grid_for(long long total) {
 }  // namespace
 
 #define STREAM reinterpret_cast<cudaStream_t>(stream)
+
+extern "C" int ladi_clip_preprocess(const float* x, int n, int c, int h, int w, int oh, int ow, const float* mean, const float* stdev,
+                                    int quantise, float* out, void* stream) {
+  LADI_CHECK(x && out && mean && stdev && n > 0 && c > 0 && h > 0 && w > 0 && oh > 0 && ow > 0, "clip_preprocess: bad extent");
+  LADI_CHECK((float)h / oh <= 5.f && (float)w / ow <= 5.f, "clip_preprocess: down-scale factors above 5 are not supported");
+  LADI_CUDA(ladi_launch(clip_preprocess_kernel, dim3(grid_for((long long)n * oh * ow)), dim3(256), 0, STREAM, x, n, c, h, w, oh, ow, mean,
+                        stdev, quantise, out));
+  return LADI_OK;
+}
 
 extern "C" int ladi_resize_aa(const float* x, int n, int c, int h, int w, int oh, int ow, void* out, int out_pitch, int c_off, void* stream) {
   LADI_CHECK(x && out && n > 0 && c > 0 && h > 0 && w > 0 && oh > 0 && ow > 0, "resize_aa: bad extent");

@@ -62,6 +62,7 @@ SIGNATURES = {
     "ladi_patchify": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "ladi_vit_assemble": ([_P, _I, _P, _P, _P, _I, _I, _I, _P], _I),
     "ladi_resize_aa": ([_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P], _I),
+    "ladi_clip_preprocess": ([_P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P], _I),
     "ladi_space_to_depth2": ([_P, _I, _I, _I, _I, _I, _P, _I, _P], _I),
     "ladi_channel_affine": ([_P, _L, _I, _I, _P, _P, _P], _I),
     "ladi_l2norm_channels": ([_P, _L, _I, _I, _P], _I),

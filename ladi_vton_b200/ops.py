@@ -342,6 +342,15 @@ def resize_aa(x, oh, ow, out=None, c_off=0):
     return out
 
 
+def clip_preprocess(x, oh, ow, mean, std, quantise=False):
+    """inference.py:265-271: resize((x + 1) / 2, (oh, ow), antialias=True).clamp(0, 1) -> (v - mean) / std; NCHW fp32 in and out."""
+    n, c, h, w = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and mean.numel() == c and std.numel() == c
+    out = torch.empty((n, c, oh, ow), dtype=torch.float32, device=x.device)
+    _call("ladi_clip_preprocess", 0.0, _ptr(x), n, c, h, w, oh, ow, _ptr(mean), _ptr(std), int(bool(quantise)), _ptr(out), _stream())
+    return out
+
+
 def space_to_depth2(x, c=None):
     """NHWC bf16 [n,h,w,pitch] (first c channels) -> [n,h/2,w/2,pad8(4c)] with channel (sy*2+sx)*c + ch; returns (tensor, 4c)."""
     n, h, w, cc, pitch = _nhwc(x)

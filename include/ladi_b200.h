@@ -85,6 +85,8 @@ typedef struct ladi_conv_desc {
   int force_direct_epilogue; /* 1 = direct-store epilogue even where the staged TMA-store epilogue applies (tests) */
   void* splitk_ws;           /* optional fp32 workspace: enables split-K for few-tile / long-K shapes (NULL = never split) */
   int64_t splitk_ws_bytes;
+  int pair_mode;             /* CTA pairs (tcgen05 cta_group::2, M = 256 across the two SMs of a TPC, each staging half of B):
+                                0 = library default (env LADI_CONV_2CTA), 1 = force (error if the shape cannot pair), 2 = never */
 } ladi_conv_desc;
 LADI_API int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream);
 

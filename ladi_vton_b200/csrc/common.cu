@@ -88,3 +88,12 @@ int ladi_pdl_enabled() {
   }
   return v;
 }
+
+int ladi_conv_pair_default() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LADI_CONV_2CTA");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}

@@ -38,6 +38,7 @@ int ladi_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const ui
 
 int ladi_num_sms();
 int ladi_pdl_enabled();  // env LADI_PDL=0 disables programmatic dependent launch (A/B timing)
+int ladi_conv_pair_default();  // env LADI_CONV_2CTA: 0 = single-CTA MMAs only, 1 = CTA-pair (cta_group::2) kernels where they apply
 
 #ifdef __CUDACC__
 #include <utility>
@@ -51,6 +52,21 @@ inline cudaError_t ladi_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = ladi_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+// Same, as thread-block clusters of `cluster_x` CTAs along x (grid.x must be a multiple of it).
+template <typename... KArgs, typename... Args>
+inline cudaError_t ladi_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, unsigned cluster_x, size_t smem, cudaStream_t stream,
+                                       Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ladi_pdl_enabled() ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 #endif

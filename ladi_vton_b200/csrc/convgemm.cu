@@ -108,13 +108,18 @@ __device__ __forceinline__ TileCoord tile_coord(const KParams& p, int tile) {
   return t;
 }
 
-template <int BN>
+// PAIR = true: launched as clusters of two CTAs (the two SMs of a TPC) that execute tcgen05.mma.cta_group::2 with M = 256: the
+// cluster owns two M tiles (one per CTA) of the same N tile; each CTA stages its own 128 A rows and HALF of the B rows, so the
+// shared-memory traffic per MMA (TMA writes + operand reads) drops from A + B to A + B/2.  Only the leader issues MMAs; the
+// epilogue is per CTA and identical to the single-CTA kernel.
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(384, 1)
 convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ EMaps emaps,
                 const __grid_constant__ KParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int B_ROWS = PAIR ? BN / 2 : BN;   // B rows staged by this CTA
+  constexpr int B_BYTES = B_ROWS * BK * 2;
   constexpr uint32_t ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;  // TMEM columns per accumulator
   constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;
   const int STAGES = p.stages;
@@ -129,6 +134,8 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4 + RES_BUFS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;      // 0 = leader (issues the MMAs)
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) ptx::prefetch_tmap(&amaps.m[p.seg[s].map]);
@@ -143,26 +150,46 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull0 + 8 * a, 1);
-      ptx::mbar_init(tempty0 + 8 * a, 256);
+      ptx::mbar_init(tempty0 + 8 * a, PAIR ? 512 : 256);  // PAIR: the epilogue threads of BOTH CTAs release the leader's accumulator
     }
     for (int a = 0; a < RES_BUFS; ++a) ptx::mbar_init(rfull0 + 8 * a, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), TMEM_COLS);
+  if (warp == 2) {
+    if constexpr (PAIR) ptx::tmem_alloc_pair(ptx::smem_u32(tmem_slot), TMEM_COLS);
+    else ptx::tmem_alloc(ptx::smem_u32(tmem_slot), TMEM_COLS);
+  }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync();  // the peer's barriers are initialised before anything is signalled across the pair
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   ptx::pdl_wait();  // everything above overlapped the previous kernel's tail; its results are visible from here on
 
-  const int num_tiles = p.tiles_m * p.tiles_n;
-  const int num_items = num_tiles * p.splits;
+  // work items: single CTA = (tile, K split); pair = (pair of M tiles, N tile), this CTA taking M tile 2*pm + rank (a phantom tile
+  // past the end when tiles_m is odd: its loads are zero-filled and its stores clipped by the TMA unit / the row_ok mask)
+  const int num_items = PAIR ? ((p.tiles_m + 1) >> 1) * p.tiles_n : p.tiles_m * p.tiles_n * p.splits;
+  auto item_tile = [&](int item) -> int {
+    if constexpr (PAIR) {
+      const int pm = item / p.tiles_n;
+      return (2 * pm + (int)rank) * p.tiles_n + (item - pm * p.tiles_n);
+    } else {
+      return item / p.splits;
+    }
+  };
+  // the leader's barriers as shared::cluster addresses (what the peer signals)
+  const uint32_t full_leader0 = PAIR ? ptx::mapa(full0, 0) : full0;
+  const uint32_t tempty_leader0 = PAIR ? ptx::mapa(tempty0, 0) : tempty0;
+  auto release_acc = [&](uint32_t as) {
+    if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty_leader0 + 8 * as);
+    else ptx::mbar_arrive(tempty0 + 8 * as);
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (warp-uniform loop, one elected lane issues)
     uint32_t stage = 0, phase = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int tile = item / p.splits, split = item - tile * p.splits;
+    for (int item = worker; item < num_items; item += nworkers) {
+      const int tile = item_tile(item), split = PAIR ? 0 : item - tile * p.splits;
       const int kb0 = split * p.kb_per_split, kb1 = min(p.total_kb, kb0 + p.kb_per_split);
       const TileCoord tc = tile_coord(p, tile);
       int kb = 0;
@@ -175,23 +202,31 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
           ptx::mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t fb = full0 + 8 * stage;
           if (ptx::elect_one()) {
-            ptx::mbar_expect_tx(fb, A_BYTES + B_BYTES);
-            ptx::tma_load_4d(am, ptx::smem_u32(sA + stage * A_BYTES), fb, sg.c_begin + c * BK, tc.x0 + sg.dx, tc.y0 + sg.dy, tc.n0);
-            ptx::tma_load_2d(&tmB, ptx::smem_u32(sB + stage * B_BYTES), fb, kb * BK, tc.nt * BN);
+            if constexpr (PAIR) {
+              // both CTAs' bytes are credited to the leader's barrier, which alone expects them
+              if (rank == 0) ptx::mbar_expect_tx(fb, 2 * (A_BYTES + B_BYTES));
+              const uint32_t fl = full_leader0 + 8 * stage;
+              ptx::tma_load_4d_pair(am, ptx::smem_u32(sA + stage * A_BYTES), fl, sg.c_begin + c * BK, tc.x0 + sg.dx, tc.y0 + sg.dy, tc.n0);
+              ptx::tma_load_2d_pair(&tmB, ptx::smem_u32(sB + stage * B_BYTES), fl, kb * BK, tc.nt * BN + (int)rank * B_ROWS);
+            } else {
+              ptx::mbar_expect_tx(fb, A_BYTES + B_BYTES);
+              ptx::tma_load_4d(am, ptx::smem_u32(sA + stage * A_BYTES), fb, sg.c_begin + c * BK, tc.x0 + sg.dx, tc.y0 + sg.dy, tc.n0);
+              ptx::tma_load_2d(&tmB, ptx::smem_u32(sB + stage * B_BYTES), fb, kb * BK, tc.nt * BN);
+            }
           }
           __syncwarp();
           if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && rank == 0) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
-    constexpr uint32_t idesc = ptx::idesc_bf16(BM, BN, 0, 0);
+    constexpr uint32_t idesc = ptx::idesc_bf16(PAIR ? 2 * BM : BM, BN, 0, 0);
     uint32_t stage = 0, phase = 0;
     int it = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+    for (int item = worker; item < num_items; item += nworkers, ++it) {
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-      const int split = item % p.splits;
+      const int split = PAIR ? 0 : item % p.splits;
       const int nkb = min(p.total_kb, (split + 1) * p.kb_per_split) - split * p.kb_per_split;
       ptx::mbar_wait(tempty0 + 8 * as, aphase ^ 1);
       ptx::tc_fence_after();
@@ -202,11 +237,19 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
         const uint64_t adesc = ptx::smem_desc_sw128(ptx::smem_u32(sA + stage * A_BYTES));
         const uint64_t bdesc = ptx::smem_desc_sw128(ptx::smem_u32(sB + stage * B_BYTES));
         if (ptx::elect_one()) {
+          if constexpr (PAIR) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            ptx::mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          ptx::mma_commit(empty0 + 8 * stage);  // smem slot reusable once these MMAs have read it
-          if (kb == nkb - 1) ptx::mma_commit(tfull0 + 8 * as);  // accumulator complete
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              ptx::mma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            ptx::mma_commit_pair(empty0 + 8 * stage, 3);                    // both CTAs' slots are reusable
+            if (kb == nkb - 1) ptx::mma_commit_pair(tfull0 + 8 * as, 3);    // both CTAs' accumulator halves are complete
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              ptx::mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            ptx::mma_commit(empty0 + 8 * stage);  // smem slot reusable once these MMAs have read it
+            if (kb == nkb - 1) ptx::mma_commit(tfull0 + 8 * as);  // accumulator complete
+          }
         }
         __syncwarp();
         if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
@@ -236,11 +279,11 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
       const int sw128 = r & 7, sw64 = (r >> 1) & 3;
       const int BNo = geglu ? BN / 2 : BN;                // output columns per tile
       // residual producer cursor (elected thread): runs up to RES_BUFS slabs ahead of the consumers, across tile boundaries
-      int ptile = blockIdx.x, pslab = 0;
+      int pitem = worker, pslab = 0;
       uint32_t pcount = 0;
       auto issue_residual = [&]() {
-        if (ptile >= num_tiles) return;
-        const TileCoord pc = tile_coord(p, ptile);
+        if (pitem >= num_items) return;
+        const TileCoord pc = tile_coord(p, item_tile(pitem));
         const int pvalid = min(BN, p.c_out - pc.nt * BN);
         const int pnslabs = (pvalid + acc_per_slab - 1) / acc_per_slab;
         const int w = min(64, BNo - 64 * pslab);
@@ -250,14 +293,14 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
         ptx::tma_load_4d(w == 64 ? &emaps.res64 : &emaps.res32, ptx::smem_u32(sRes + slot * SLAB_BYTES), rb, pc.nt * BNo + 64 * pslab, pc.x0,
                          pc.y0, pc.n0);
         ++pcount;
-        if (++pslab == pnslabs) { pslab = 0; ptile += gridDim.x; }
+        if (++pslab == pnslabs) { pslab = 0; pitem += nworkers; }
       };
       if (has_res && elected)
         for (int i = 0; i < RES_BUFS; ++i) issue_residual();
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int item = worker; item < num_items; item += nworkers, ++it) {   // staged epilogue: never split-K, item == tile (or pair)
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-        const TileCoord tc = tile_coord(p, tile);
+        const TileCoord tc = tile_coord(p, item_tile(item));
         const int acc0 = tc.nt * BN;                                  // first accumulator column of this tile (global)
         const int acc_valid = min(BNo_full, p.c_out - acc0);
         const int nslabs = (acc_valid + acc_per_slab - 1) / acc_per_slab;
@@ -284,7 +327,7 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
           const bool last_slab = (s == nslabs - 1);
           if (last_slab && half >= nchunks) {                         // 32-column tail slab: warpgroup 1 has no chunk, release TMEM
             ptx::tc_fence_before();
-            ptx::mbar_arrive(tempty0 + 8 * as);
+            release_acc(as);
           }
 #pragma unroll 1
           for (int c = half; c < nchunks; c += 2) {
@@ -294,7 +337,7 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
             ptx::tmem_wait_ld();
             if (last_slab && c + 2 >= nchunks) {                     // this thread's last read of the accumulator: hand it back
               ptx::tc_fence_before();
-              ptx::mbar_arrive(tempty0 + 8 * as);
+              release_acc(as);
             }
             float f[32];
 #pragma unroll
@@ -369,9 +412,9 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
     } else {
       // ================= direct-store epilogue (fp32 outputs, tiny / unaligned N); the two warpgroups alternate 32-column chunks ==
       int it = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      for (int item = worker; item < num_items; item += nworkers, ++it) {
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-        const int tile = item / p.splits, split = item - tile * p.splits;
+        const int tile = item_tile(item), split = PAIR ? 0 : item - tile * p.splits;
         const TileCoord tc = tile_coord(p, tile);
         const int nt = tc.nt;
         const int n = tc.n0 + rn, y = tc.y0 + ry, x = tc.x0 + rx;
@@ -455,7 +498,7 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
           }
         }
         ptx::tc_fence_before();
-        ptx::mbar_arrive(tempty0 + 8 * as);
+        release_acc(as);
       }
     }
   }
@@ -463,10 +506,12 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
   __syncwarp();
   ptx::pdl_trigger();
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) ptx::cluster_sync();  // neither CTA frees tensor memory / exits while the other may still signal or read it
+  else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (PAIR) ptx::tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -505,23 +550,42 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 constexpr size_t SMEM_LIMIT = 232448;  // 227 KiB per CTA
 constexpr size_t SMEM_TAIL = (2 * MAX_STAGES + 4 + RES_BUFS) * 8 + 16 + 1024;  // barriers + TMEM slot + alignment slack
 
-template <int BN>
+template <int BN, bool PAIR>
 int launch(const AMaps& am, const CUtensorMap& tmB, const EMaps& em, KParams& kp, cudaStream_t stream) {
   static bool attr_set = false;
+  static int max_clusters = 0;
   if (!attr_set) {
-    LADI_CUDA(cudaFuncSetAttribute(convgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    LADI_CUDA(cudaFuncSetAttribute(convgemm_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT));
+    if (PAIR) {  // how many CTA pairs can be co-resident (one CTA per SM, both SMs of a TPC): the persistent grid size
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * ladi_num_sms()); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = SMEM_LIMIT;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&max_clusters, convgemm_kernel<BN, PAIR>, &cfg) != cudaSuccess || max_clusters <= 0) {
+        (void)cudaGetLastError();
+        max_clusters = ladi_num_sms() / 2;
+      }
+    }
     attr_set = true;
   }
   const size_t staging = kp.staged ? (size_t)(kp.residual != nullptr ? 2 + RES_BUFS : 2) * SLAB_BYTES : 0;
-  const size_t per_stage = A_BYTES + (size_t)BN * BK * 2;
+  const size_t per_stage = A_BYTES + (size_t)(PAIR ? BN / 2 : BN) * BK * 2;
   int stages = (int)((SMEM_LIMIT - SMEM_TAIL - staging) / per_stage);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   LADI_CHECK(stages >= 2, "not enough shared memory for a 2-stage pipeline");
   kp.stages = stages;
   const size_t smem = stages * per_stage + staging + SMEM_TAIL;
+  if (PAIR) {
+    const int items = ((kp.tiles_m + 1) / 2) * kp.tiles_n;
+    const int clusters = items < max_clusters ? items : max_clusters;
+    LADI_CUDA(ladi_launch_cluster(convgemm_kernel<BN, PAIR>, dim3(2 * clusters), dim3(384), 2u, smem, stream, am, tmB, em, kp));
+    return LADI_OK;
+  }
   const int tiles = kp.tiles_m * kp.tiles_n * kp.splits;
   const int grid = tiles < ladi_num_sms() ? tiles : ladi_num_sms();
-  LADI_CUDA(ladi_launch(convgemm_kernel<BN>, dim3(grid), dim3(384), smem, stream, am, tmB, em, kp));
+  LADI_CUDA(ladi_launch(convgemm_kernel<BN, PAIR>, dim3(grid), dim3(384), smem, stream, am, tmB, em, kp));
   return LADI_OK;
 }
 
@@ -682,11 +746,20 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
   }
   kp.tiles_n = (d->c_out + BN - 1) / BN;
 
+  // ---- CTA pairs (tcgen05 cta_group::2): two M tiles per cluster share one N tile; needs >= 2 M tiles, no split-K, and a B half
+  // of whole 8-row swizzle groups.  pair_mode: 0 = library default (env LADI_CONV_2CTA), 1 = force, 2 = never.
+  bool pair = false;
+  if (!split && kp.tiles_m >= 2 && BN >= 128 && BN % 16 == 0) {
+    if (d->pair_mode == 1) pair = true;
+    else if (d->pair_mode == 0 && ladi_conv_pair_default()) pair = (long)kp.tiles_m * kp.tiles_n >= sms / 2;
+  }
+  LADI_CHECK(d->pair_mode != 1 || pair, "pair_mode=1 needs >= 2 M tiles, BN >= 128 and no split-K (BN=%d, tiles_m=%d)", BN, kp.tiles_m);
+
   CUtensorMap tmB;
   {
     const uint64_t dims[2] = {(uint64_t)d->k_total, (uint64_t)d->c_out};
     const uint64_t strides[1] = {(uint64_t)d->weight_pitch * 2};
-    const uint32_t bbox[2] = {(uint32_t)BK, (uint32_t)BN};
+    const uint32_t bbox[2] = {(uint32_t)BK, (uint32_t)(pair ? BN / 2 : BN)};
     if (ladi_encode_tmap_bf16(&tmB, d->weight, 2, dims, strides, bbox)) return LADI_ERR_CUDA;
   }
   if (kp.staged) {
@@ -705,12 +778,12 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
   }
   int rc = LADI_OK;
   switch (BN) {
-    case 256: rc = launch<256>(am, tmB, em, kp, stream); break;
-    case 192: rc = launch<192>(am, tmB, em, kp, stream); break;
-    case 160: rc = launch<160>(am, tmB, em, kp, stream); break;
-    case 128: rc = launch<128>(am, tmB, em, kp, stream); break;
-    case 64: rc = launch<64>(am, tmB, em, kp, stream); break;
-    case 32: rc = launch<32>(am, tmB, em, kp, stream); break;
+    case 256: rc = pair ? launch<256, true>(am, tmB, em, kp, stream) : launch<256, false>(am, tmB, em, kp, stream); break;
+    case 192: rc = pair ? launch<192, true>(am, tmB, em, kp, stream) : launch<192, false>(am, tmB, em, kp, stream); break;
+    case 160: rc = pair ? launch<160, true>(am, tmB, em, kp, stream) : launch<160, false>(am, tmB, em, kp, stream); break;
+    case 128: rc = pair ? launch<128, true>(am, tmB, em, kp, stream) : launch<128, false>(am, tmB, em, kp, stream); break;
+    case 64: rc = launch<64, false>(am, tmB, em, kp, stream); break;
+    case 32: rc = launch<32, false>(am, tmB, em, kp, stream); break;
     default: LADI_CHECK(false, "unsupported BN %d", BN);
   }
   if (rc != LADI_OK || !split) return rc;

@@ -22,6 +22,7 @@ class ConvDesc(C.Structure):
         ("residual", C.c_void_p), ("residual_pitch", C.c_int),
         ("row_scale", C.c_void_p), ("act", C.c_int),
         ("out", C.c_void_p), ("out_pitch", C.c_int), ("out_fp32", C.c_int), ("force_bn", C.c_int), ("force_direct_epilogue", C.c_int), ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64),
+        ("pair_mode", C.c_int),
     ]
 
 

@@ -63,7 +63,7 @@ def padded_k(channels):
 
 def conv2d(srcs, weight, c_out, *, ksize=3, stride=1, pad_lo=1, shortcut=(), bias=None, bias_per_row=False,
            bias_step_stride=0, step_ptr=None, residual=None, row_scale=None, act=ACT_NONE, out=None, out_fp32=False,
-           force_bn=0, direct_epilogue=False, split_k=True):
+           force_bn=0, direct_epilogue=False, split_k=True, pair=None):
     """Implicit-GEMM convolution over the channel-concat of `srcs` (+ fused 1x1 over `shortcut` tensors).
     `weight`: packed bf16 [c_out, k_total] (see weights.pack_conv).  Returns the NHWC output tensor."""
     assert 1 <= len(srcs) <= 2 and len(shortcut) <= 2
@@ -108,6 +108,7 @@ def conv2d(srcs, weight, c_out, *, ksize=3, stride=1, pad_lo=1, shortcut=(), bia
         d.row_scale = row_scale.data_ptr()
     d.act, d.out, d.out_pitch, d.out_fp32, d.force_bn = act, out.data_ptr(), op, int(out_fp32), force_bn
     d.force_direct_epilogue = int(direct_epilogue)
+    d.pair_mode = 0 if pair is None else (1 if pair else 2)  # CTA pairs (cta_group::2): None = library default (env LADI_CONV_2CTA)
     if split_k:
         ws = splitk_workspace(srcs[0].device)
         d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), ws.numel() * 4

@@ -340,3 +340,96 @@ def test_ddim_cfg_step(cuda, cfg):
     assert torch.equal(uin[:B, ..., :4], ref.bfloat16().permute(0, 2, 3, 1))
     if cfg:
         assert torch.equal(uin[B:, ..., :4], uin[:B, ..., :4])
+
+
+# ------------------------------------------------------------------------------------------------ CTA pairs (tcgen05 cta_group::2)
+@pytest.mark.parametrize("M,K,N,bn", [(512, 320, 320, 160), (640, 256, 512, 256), (384, 1024, 640, 128), (300, 320, 640, 192),
+                                      (3072 * 4, 320, 960, 0), (128 * 5, 128, 256, 256), (128 * 149, 64, 320, 160)])
+@pytest.mark.parametrize("direct", [False, True])
+def test_gemm_pair(cuda, M, K, N, bn, direct):
+    """Same GEMMs through the CTA-pair kernel (M = 256 MMAs across two SMs, each staging half of B): odd numbers of M tiles (phantom
+    tile of the last pair), ragged M (300 rows), N tiles that overhang c_out, more pairs than clusters (persistent loop)."""
+    from ladi_vton_b200 import ops, weights
+    a = rnd((M, K), cuda, 1).bfloat16()
+    w = rnd((N, K), cuda, 2, K ** -0.5)
+    b = rnd((N,), cuda, 3)
+    y = ops.gemm(a, weights.pack_linear(w), N, bias=b, force_bn=bn, direct_epilogue=direct, pair=True, split_k=False)
+    y1 = ops.gemm(a, weights.pack_linear(w), N, bias=b, force_bn=bn, direct_epilogue=direct, pair=False, split_k=False)
+    ref = a.float() @ w.bfloat16().float().t() + b
+    torch.cuda.synchronize()
+    assert nerr(y, ref) < TOL_BF16
+    assert torch.equal(y, y1)  # same products in the same order: the pair kernel is bit-identical to the single-CTA kernel
+
+
+@pytest.mark.parametrize("mode", ["residual", "silu", "geglu", "fp32", "rowscale", "stepbias"])
+def test_gemm_pair_epilogues(cuda, mode):
+    from ladi_vton_b200 import ops, weights
+    M, K, N = 128 * 7 + 40, 320, 640
+    a = rnd((M, K), cuda, 1).bfloat16()
+    w = rnd((N, K), cuda, 2, K ** -0.5)
+    b = rnd((N,), cuda, 3)
+    base = a.float() @ w.bfloat16().float().t() + b
+    kw = dict(pair=True, split_k=False)
+    if mode == "residual":
+        r = rnd((M, N), cuda, 4).bfloat16()
+        y, ref = ops.gemm(a, weights.pack_linear(w), N, bias=b, residual=r, **kw), base + r.float()
+    elif mode == "silu":
+        y, ref = ops.gemm(a, weights.pack_linear(w), N, bias=b, act=ops.ACT_SILU, **kw), F.silu(base)
+    elif mode == "geglu":
+        wi, bi = weights.interleave_geglu(w, b)
+        y = ops.gemm(a, weights.pack_linear(wi), N, bias=bi.contiguous(), act=ops.ACT_GEGLU, **kw)
+        v, g = base.chunk(2, dim=-1)
+        ref = v * F.gelu(g)
+    elif mode == "fp32":
+        y, ref = ops.gemm(a, weights.pack_linear(w), N, bias=b, out_fp32=True, **kw), base
+    elif mode == "rowscale":
+        rs = torch.rand(M, device=cuda)
+        y, ref = ops.gemm(a, weights.pack_linear(w), N, bias=b, row_scale=rs, **kw), base * rs[:, None]
+    else:
+        tab = rnd((5, N), cuda, 6)
+        step = torch.tensor([3, 0], dtype=torch.int32, device=cuda)
+        y = ops.gemm(a, weights.pack_linear(w), N, bias=tab, bias_step_stride=N, step_ptr=step, **kw)
+        ref = a.float() @ w.bfloat16().float().t() + tab[3]
+    torch.cuda.synchronize()
+    assert nerr(y, ref) < (TOL_F32 if mode == "fp32" else TOL_BF16)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 64, 48, 320, 320), (2, 32, 24, 192, 640), (1, 128, 96, 64, 128), (3, 24, 20, 192, 192),
+                                            (16, 32, 24, 640, 640)])
+def test_conv3x3_pair(cuda, n, h, w, cin, cout):
+    from ladi_vton_b200 import ops, weights
+    x = rnd((n, h, w, cin), cuda, 1).bfloat16()
+    res = rnd((n, h, w, cout), cuda, 5).bfloat16()
+    wt = rnd((cout, cin, 3, 3), cuda, 2, (9 * cin) ** -0.5)
+    b = rnd((cout,), cuda, 3)
+    wp = weights.pack_conv(wt, [cin])
+    y = ops.conv2d([x], wp, cout, bias=b, residual=res, pair=True, split_k=False)
+    y1 = ops.conv2d([x], wp, cout, bias=b, residual=res, pair=False, split_k=False)
+    ref = conv_ref([x], wt, b) + res.float()
+    torch.cuda.synchronize()
+    assert nerr(y, ref) < TOL_BF16
+    assert torch.equal(y, y1)
+
+
+def test_conv_pair_concat_shortcut_stride2(cuda):
+    """UNet up-block conv1 (two concatenated sources + fused 1x1 shortcut) and a stride-2 downsample through the pair kernel."""
+    from ladi_vton_b200 import ops, weights
+    n, h, w, c1, c2, cout = 2, 32, 24, 128, 64, 256
+    x1, x2 = rnd((n, h, w, c1), cuda, 1).bfloat16(), rnd((n, h, w, c2), cuda, 2).bfloat16()
+    wt = rnd((cout, c1 + c2, 3, 3), cuda, 3, (9 * (c1 + c2)) ** -0.5)
+    b = rnd((cout,), cuda, 4)
+    y = ops.conv2d([x1, x2], weights.pack_conv(wt, [c1, c2]), cout, bias=b, pair=True, split_k=False)
+    torch.cuda.synchronize()
+    assert nerr(y, conv_ref([x1, x2], wt, b)) < TOL_BF16
+    ws = rnd((cout, c1, 3, 3), cuda, 5, (9 * c1) ** -0.5)
+    y = ops.conv2d([x1], weights.pack_conv(ws, [c1]), cout, bias=b, stride=2, pair=True, split_k=False)
+    torch.cuda.synchronize()
+    assert nerr(y, conv_ref([x1], ws, b, stride=2)) < TOL_BF16
+
+
+def test_pair_mode_errors(cuda):
+    from ladi_vton_b200 import ops, weights
+    a = rnd((100, 64), cuda, 1).bfloat16()  # one M tile: nothing to pair
+    w = weights.pack_linear(rnd((128, 64), cuda, 2))
+    with pytest.raises(RuntimeError, match="pair_mode=1"):
+        ops.gemm(a, w, 128, force_bn=128, pair=True)

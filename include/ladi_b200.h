@@ -86,7 +86,8 @@ typedef struct ladi_conv_desc {
   void* splitk_ws;           /* optional fp32 workspace: enables split-K for few-tile / long-K shapes (NULL = never split) */
   int64_t splitk_ws_bytes;
   int pair_mode;             /* CTA pairs (tcgen05 cta_group::2, M = 256 across the two SMs of a TPC, each staging half of B):
-                                0 = library default (env LADI_CONV_2CTA), 1 = force (error if the shape cannot pair), 2 = never */
+                                0 = library default (pairs when the shape allows; env LADI_CONV_2CTA=0 disables), 1 = force (error if the shape
+                                cannot pair), 2 = never */
 } ladi_conv_desc;
 LADI_API int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream);
 

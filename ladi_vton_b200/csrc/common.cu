@@ -93,7 +93,7 @@ int ladi_conv_pair_default() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("LADI_CONV_2CTA");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;  // on unless LADI_CONV_2CTA=0 (A/B timing, tools/pair_bench.py)
   }
   return v;
 }

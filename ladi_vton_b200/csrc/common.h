@@ -38,7 +38,7 @@ int ladi_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const ui
 
 int ladi_num_sms();
 int ladi_pdl_enabled();  // env LADI_PDL=0 disables programmatic dependent launch (A/B timing)
-int ladi_conv_pair_default();  // env LADI_CONV_2CTA: 0 = single-CTA MMAs only, 1 = CTA-pair (cta_group::2) kernels where they apply
+int ladi_conv_pair_default();  // 1 = CTA-pair (cta_group::2) conv kernels where they apply (default); env LADI_CONV_2CTA=0 -> single-CTA only
 
 #ifdef __CUDACC__
 #include <utility>

@@ -747,11 +747,13 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
   kp.tiles_n = (d->c_out + BN - 1) / BN;
 
   // ---- CTA pairs (tcgen05 cta_group::2): two M tiles per cluster share one N tile; needs >= 2 M tiles, no split-K, and a B half
-  // of whole 8-row swizzle groups.  pair_mode: 0 = library default (env LADI_CONV_2CTA), 1 = force, 2 = never.
+  // of whole 8-row swizzle groups.  pair_mode: 0 = library default (on; env LADI_CONV_2CTA=0 turns it off), 1 = force, 2 = never.
   bool pair = false;
   if (!split && kp.tiles_m >= 2 && BN >= 128 && BN % 16 == 0) {
     if (d->pair_mode == 1) pair = true;
-    else if (d->pair_mode == 0 && ladi_conv_pair_default()) pair = (long)kp.tiles_m * kp.tiles_n >= sms / 2;
+    // default: pair whenever there are enough M tiles that the phantom tile of an odd count is noise (measured 1.03-1.26x on every
+    // UNet shape, profiles/r01_pair_bench.jsonl)
+    else if (d->pair_mode == 0 && ladi_conv_pair_default()) pair = kp.tiles_m >= 4 && (kp.tiles_m % 2 == 0 || kp.tiles_m >= 16);
   }
   LADI_CHECK(d->pair_mode != 1 || pair, "pair_mode=1 needs >= 2 M tiles, BN >= 128 and no split-K (BN=%d, tiles_m=%d)", BN, kp.tiles_m);
 

@@ -108,7 +108,7 @@ def conv2d(srcs, weight, c_out, *, ksize=3, stride=1, pad_lo=1, shortcut=(), bia
         d.row_scale = row_scale.data_ptr()
     d.act, d.out, d.out_pitch, d.out_fp32, d.force_bn = act, out.data_ptr(), op, int(out_fp32), force_bn
     d.force_direct_epilogue = int(direct_epilogue)
-    d.pair_mode = 0 if pair is None else (1 if pair else 2)  # CTA pairs (cta_group::2): None = library default (env LADI_CONV_2CTA)
+    d.pair_mode = 0 if pair is None else (1 if pair else 2)  # CTA pairs (cta_group::2): None = library default (on where the shape allows)
     if split_k:
         ws = splitk_workspace(srcs[0].device)
         d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), ws.numel() * 4

@@ -369,7 +369,7 @@ def test_gemm_pair_epilogues(cuda, mode):
     w = rnd((N, K), cuda, 2, K ** -0.5)
     b = rnd((N,), cuda, 3)
     base = a.float() @ w.bfloat16().float().t() + b
-    kw = dict(pair=True, split_k=False)
+    kw = dict(pair=True, split_k=False, force_bn=128 if mode == "geglu" else 160)
     if mode == "residual":
         r = rnd((M, N), cuda, 4).bfloat16()
         y, ref = ops.gemm(a, weights.pack_linear(w), N, bias=b, residual=r, **kw), base + r.float()

@@ -61,7 +61,7 @@ def main():
             ts.sort()
             us = ts[len(ts) // 2] * 1e3
             line[name + "_us"] = round(us, 1)
-            line[name + "_tflops"] = round(line["gflop"] / us * 1e3 / 1e3, 1)
+            line[name + "_tflops"] = round(line["gflop"] * 1e9 / (us * 1e-6) / 1e12, 1)
             outs[name] = out.clone()
         line["bit_identical"] = bool(torch.equal(outs["single"], outs["pair"]))
         line["speedup"] = round(line["single_us"] / line["pair_us"], 3)

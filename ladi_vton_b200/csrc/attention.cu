@@ -8,14 +8,17 @@
 // projection output are read in place (no head split/transposes); out-of-range tokens are zero-filled and masked.
 //
 // Two kernels:
-//   attention_pair_kernel  (nkv > 128): one CTA owns TWO 128-row query tiles with one softmax warpgroup each ("ping-pong"):
-//       the MMA thread interleaves  PV_A(j), S_A(j+1), PV_B(j), S_B(j+1)  so the tensor core works on one tile while the other
-//       tile's warpgroup is in its softmax; K/V tiles are loaded once for both query tiles (2-stage TMA ring).
+//   attention_pair_kernel  (nkv > 128): one CTA owns TWO 128-row query tiles, each with its own softmax warps AND its own MMA issuer
+//       warp, so each tile's chain  softmax(j) -> S(j+1), P(j) V(j) -> softmax(j+1)  advances independently and the tensor core works
+//       on one tile while the other is in its softmax; S(j+1) is issued before P(j) V(j) (shortest path back to the softmax warps);
+//       K/V tiles are loaded once for both query tiles (3-stage TMA ring, released when both issuers are done with a tile).
 //   attention_single_kernel<SHORT>: one query tile per CTA; SHORT (nkv <= 128, e.g. the 77 text tokens of cross-attention)
 //       needs one K/V stage and 256 TMEM columns, so two CTAs share an SM and hide each other's latency chain.
 //
 // Replaces diffusers CrossAttention (attn1/attn2 of BasicTransformerBlock) inside UNet2DConditionModel.forward, which the
 // reference runs through torch SDPA or xformers (/root/reference/src/inference.py:143-147; call-site tryon_pipe.py:732).
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -30,6 +33,7 @@ struct AttnParams {
   int out_pitch;
   int64_t out_batch_stride;
   float scale_log2;  // scale * log2(e)
+  int b_delay;       // pair kernel: cycles tile B's first S = Q K^T is held back after tile A's (phase offset of the two softmaxes)
   long long* trace;  // optional per-phase clock64() trace of CTA (0,0,0) (tools/attn_trace.py); null in production
 };
 
@@ -290,10 +294,15 @@ __device__ __forceinline__ void softmax_pair_lazy(const AttnParams& p, int n_til
   const uint32_t ts = tS + lane_off + col0;
   float m = -INFINITY, l = 0.f, alpha_pending = 1.f;
   bool rescale_pending = false;
+  const bool trace_ok = (ew == 0 && lane == 0);
+  int trace_base = 0;
   for (int j = 0; j < n_tiles; ++j) {
     const int valid = min(COLS, p.nkv - j * BKV - col0);  // may be <= 0 for the upper half of a ragged last tile
+    trace_base = 1024 * (int)(bar_id * 2 + half) + 8 * j;  // bar_id: 1 = tile A, 2 = tile B
+    TRACE(0);
     ptx::mbar_wait(s_full, j & 1);
     ptx::tc_fence_after();
+    TRACE(1);
     if (j == 0) {  // exact maximum for the first tile
       float mx = -INFINITY;
 #pragma unroll 1
@@ -310,9 +319,11 @@ __device__ __forceinline__ void softmax_pair_lazy(const AttnParams& p, int n_til
       ptx::named_barrier_sync(bar_id, 256);
       m = fmaxf(mx, xm[(half ^ 1) * 128 + r]) * p.scale_log2;
     }
-    // The tensor pipe completes MMAs in issue order and S(j) was issued after P(j-1) V: s_full(j) therefore also means
-    // that O and the P region are free again -- no separate wait on o_ready inside the loop.
+    // S(j) is issued BEFORE P(j-1) V (shorter critical chain), so O and the P region are only free again once o_ready(j-1) has
+    // completed; by the time the first 32 keys have been exponentiated that MMA group (256 cycles) is long done.
     if (j > 0 && __any_sync(0xffffffffu, rescale_pending)) {  // the reference moved at the last boundary: bring O to the new scale
+      ptx::mbar_wait(o_ready, (j - 1) & 1);
+      ptx::tc_fence_after();
       uint32_t v[32];
       ptx::tmem_ld32(tO + lane_off + half * OCOLS, v);
       ptx::tmem_wait_ld();
@@ -331,6 +342,8 @@ __device__ __forceinline__ void softmax_pair_lazy(const AttnParams& p, int n_til
         ptx::tmem_ld32(ts + c, v);
         ptx::tmem_wait_ld();
       }
+      if (c == 0) TRACE(2);
+      else TRACE(4);
       if (c + 32 <= valid) {
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
@@ -352,12 +365,19 @@ __device__ __forceinline__ void softmax_pair_lazy(const AttnParams& p, int n_til
           pk[i >> 1] = ptx::pack_bf16(p0, p1);
         }
       }
+      if (c == 0 && j > 0) {  // P(j-1) must have been consumed before it is overwritten
+        ptx::mbar_wait(o_ready, (j - 1) & 1);
+        ptx::tc_fence_after();
+      }
       ptx::tmem_st16(tP + lane_off + half * (COLS / 2) + (c >> 1), pk);
+      if (c == 0) TRACE(3);
+      else TRACE(5);
     }
     l += (s0 + s1) + (s2 + s3);
     ptx::tmem_wait_st();
     ptx::tc_fence_before();
     ptx::mbar_arrive(p_full);
+    TRACE(6);
     // ---- off the MMA critical path: agree on the reference for the next tile
     if (j + 1 < n_tiles) {
       float* slot = xm + ((j + 1) & 1) * 256;
@@ -369,6 +389,7 @@ __device__ __forceinline__ void softmax_pair_lazy(const AttnParams& p, int n_til
       alpha_pending = rescale_pending ? ex2(m - m_true) : 1.f;
       if (rescale_pending) { l *= alpha_pending; m = m_true; }
     }
+    TRACE(7);
   }
   // ---- output: O / l, row sum = sum over both column halves (identical references throughout)
   {
@@ -553,7 +574,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     ptx::mbar_init(q_full, 1);
     for (int s = 0; s < PAIR_KV_STAGES; ++s) {
       ptx::mbar_init(kv_full0 + 8 * s, 1);
-      ptx::mbar_init(kv_empty0 + 8 * s, 1);
+      ptx::mbar_init(kv_empty0 + 8 * s, has_b ? 2 : 1);  // one commit per query tile's MMA issuer
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(s_full0 + 8 * s, 1);
@@ -587,71 +608,67 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       __syncwarp();
     }
-  } else if (warp == 1) {
-    // MMA issuer: warp-uniform loop, one elected lane issues (see ptx::elect_one)
-    const uint64_t qdA = ptx::smem_desc_sw128(ptx::smem_u32(sQ)), qdB = ptx::smem_desc_sw128(ptx::smem_u32(sQ + TILE_BYTES));
-    const uint64_t pA0 = ptx::smem_desc_sw128(ptx::smem_u32(sP)), pA1 = ptx::smem_desc_sw128(ptx::smem_u32(sP + TILE_BYTES));
-    const uint64_t pB0 = ptx::smem_desc_sw128(ptx::smem_u32(sP + 2 * TILE_BYTES)),
-                   pB1 = ptx::smem_desc_sw128(ptx::smem_u32(sP + 3 * TILE_BYTES));
-    const uint32_t tSA = tmem_base, tSB = tmem_base + 128, tOA = tmem_base + 256, tOB = tmem_base + 320;
-    const uint32_t tPA = tmem_base + 384, tPB = tmem_base + 448;  // P tiles in tensor memory (PT variant)
+  } else if (warp == 1 || (warp == 3 && has_b)) {
+    // MMA issuers: ONE WARP PER QUERY TILE (warp 1 = tile A, warp 3 = tile B), each a warp-uniform loop with one elected lane
+    // issuing (see ptx::elect_one).  Each tile's chain  softmax(j) -> P V(j), S(j+1) -> softmax(j+1)  advances on its own: a single
+    // issuer serving A then B in program order forced the two tiles into lockstep (both softmaxes, then both MMA groups, measured
+    // with tools/attn_trace.py: the MUFU pipe idled through the MMA phases and the tensor pipe through the softmax phases).
+    // A K/V stage is released when BOTH issuers have committed their P V of that tile (kv_empty count 2).
+    const int wg = warp == 1 ? 0 : 1;
+    const uint64_t qd = ptx::smem_desc_sw128(ptx::smem_u32(sQ + wg * TILE_BYTES));
+    const uint64_t p0 = ptx::smem_desc_sw128(ptx::smem_u32(sP + wg * 2 * TILE_BYTES)),
+                   p1 = ptx::smem_desc_sw128(ptx::smem_u32(sP + wg * 2 * TILE_BYTES + TILE_BYTES));
+    const uint32_t tS = tmem_base + 128 * wg, tO = tmem_base + 256 + 64 * wg, tP = tmem_base + 384 + 64 * wg;  // P tile in TMEM (PT)
+    const uint32_t s_full = s_full0 + 8 * wg, p_full = p_full0 + 8 * wg, o_ready = o_ready0 + 8 * wg;
     const uint64_t k0 = ptx::smem_desc_sw128(ptx::smem_u32(sK)), v0 = ptx::smem_desc_sw128(ptx::smem_u32(sV));
     constexpr uint64_t STAGE_DESC = TILE_BYTES >> 4;  // descriptor start-address units per K/V stage
+    const bool trace_ok = (lane == 0);
+    int trace_base = 1024 * (6 + wg);
     ptx::mbar_wait(q_full, 0);
+    if (wg == 1 && p.b_delay > 0) {
+      // optional phase offset of tile B's first S = Q K^T behind tile A's (tuning knob, env LADI_ATTN_B_DELAY in cycles; measured
+      // neutral on B200 -- profiles/r01_attn_bench.jsonl -- because the two tiles drift back into phase within ~10 KV tiles)
+      ptx::mbar_wait(s_full0, 0);
+      const long long t_start = clock64();
+      while (clock64() - t_start < p.b_delay) {
+      }
+    }
     ptx::mbar_wait(kv_full0, 0);
     ptx::tc_fence_after();
     if (ptx::elect_one()) {
-      issue_qk(tSA, qdA, k0);
-      ptx::mma_commit(s_full0);
+      issue_qk(tS, qd, k0);
+      ptx::mma_commit(s_full);
     }
     __syncwarp();
-    for (int j = 0; j <= n_tiles; ++j) {
-      const uint64_t kd_j = k0 + (uint64_t)(j % PAIR_KV_STAGES) * STAGE_DESC, kd_n = k0 + (uint64_t)((j + 1) % PAIR_KV_STAGES) * STAGE_DESC;
+    for (int j = 0; j < n_tiles; ++j) {
+      trace_base = 1024 * (6 + wg) + 8 * j;
+      TRACE(0);
+      const uint64_t kd_n = k0 + (uint64_t)((j + 1) % PAIR_KV_STAGES) * STAGE_DESC;
       const uint64_t vd_j = v0 + (uint64_t)(j % PAIR_KV_STAGES) * STAGE_DESC;
-      const uint64_t vd_p = v0 + (uint64_t)((j + PAIR_KV_STAGES - 1) % PAIR_KV_STAGES) * STAGE_DESC;
-      if (j < n_tiles) {
-        // ---- tile A, KV tile j: O_A += P_A(j) V(j); then S_A(j+1) so warpgroup A can start its next softmax at once
-        ptx::mbar_wait(p_full0, j & 1);
-        ptx::tc_fence_after();
+      // K/V tile j+1 was requested two tiles ago: observe it BEFORE blocking on the softmax, off the critical chain
+      if (j + 1 < n_tiles) ptx::mbar_wait(kv_full0 + 8 * ((j + 1) % PAIR_KV_STAGES), ((j + 1) / PAIR_KV_STAGES) & 1);
+      TRACE(1);
+      ptx::mbar_wait(p_full, j & 1);  // P(j) is complete, hence S(j) has been consumed
+      ptx::tc_fence_after();
+      TRACE(2);
+      // ---- S(j+1) FIRST (the softmax warps' critical chain is  P(j) -> S(j+1) -> softmax(j+1)), then O += P(j) V(j).  The softmax
+      // of tile j+1 waits on o_ready(j) before it overwrites P or rescales O.
+      if (j + 1 < n_tiles) {
         if (ptx::elect_one()) {
-          if constexpr (PT) issue_pv_ts(tOA, tPA, vd_j, j == 0);
-          else issue_pv(tOA, pA0, pA1, vd_j, j == 0);
-          ptx::mma_commit(o_ready0);
-        }
-        __syncwarp();
-        if (j + 1 < n_tiles) {
-          ptx::mbar_wait(kv_full0 + 8 * ((j + 1) % PAIR_KV_STAGES), ((j + 1) / PAIR_KV_STAGES) & 1);
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            issue_qk(tSA, qdA, kd_n);
-            ptx::mma_commit(s_full0);
-          }
-          __syncwarp();
-        }
-      }
-      // ---- tile B, one KV tile behind
-      if (j > 0) {
-        if (has_b) {
-          ptx::mbar_wait(p_full0 + 8, (j - 1) & 1);
-          ptx::tc_fence_after();
-        }
-        if (ptx::elect_one()) {
-          if (has_b) {
-            if constexpr (PT) issue_pv_ts(tOB, tPB, vd_p, j == 1);
-            else issue_pv(tOB, pB0, pB1, vd_p, j == 1);
-            ptx::mma_commit(o_ready0 + 8);
-          }
-          ptx::mma_commit(kv_empty0 + 8 * ((j - 1) % PAIR_KV_STAGES));  // both query tiles are done with KV tile j-1
+          issue_qk(tS, qd, kd_n);
+          ptx::mma_commit(s_full);
         }
         __syncwarp();
       }
-      if (has_b && j < n_tiles) {
-        if (ptx::elect_one()) {
-          issue_qk(tSB, qdB, kd_j);  // kv_full(j) was already observed for tile A
-          ptx::mma_commit(s_full0 + 8);
-        }
-        __syncwarp();
+      TRACE(3);
+      if (ptx::elect_one()) {
+        if constexpr (PT) issue_pv_ts(tO, tP, vd_j, j == 0);
+        else issue_pv(tO, p0, p1, vd_j, j == 0);
+        ptx::mma_commit(o_ready);
+        ptx::mma_commit(kv_empty0 + 8 * (j % PAIR_KV_STAGES));  // this tile is done with K/V tile j
       }
+      __syncwarp();
+      TRACE(4);
     }
   } else if (warp >= 4) {
     const int wg = (warp - 4) >> 3;         // 0 = tile A (warps 4-11), 1 = tile B (warps 12-19)
@@ -705,6 +722,15 @@ extern "C" int ladi_attention_bf16(const ladi_attn_desc* d, void* stream_) {
   p.out = reinterpret_cast<bf16*>(d->out); p.out_pitch = d->out_pitch; p.out_batch_stride = d->out_batch_stride;
   p.scale_log2 = d->scale * 1.4426950408889634f;
   p.trace = reinterpret_cast<long long*>(d->trace);
+  {
+    static int b_delay = -1;  // env LADI_ATTN_B_DELAY (cycles) for tuning (tools/attn_bench.py); default 0
+    if (b_delay < 0) {
+      const char* e = getenv("LADI_ATTN_B_DELAY");
+      b_delay = e != nullptr ? atoi(e) : 0;
+      if (b_delay < 0) b_delay = 0;
+    }
+    p.b_delay = b_delay;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     LADI_CUDA(cudaFuncSetAttribute(attention_single_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE));

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libladi_b200.so")
+LIB_PATH = os.environ.get("LADI_B200_LIB") or os.path.join(_HERE, "libladi_b200.so")  # override: instrumented debug builds (tools/attn_trace.py)
 
 
 class ConvDesc(C.Structure):

@@ -394,17 +394,17 @@ def test_gemm_pair_epilogues(cuda, mode):
     assert nerr(y, ref) < (TOL_F32 if mode == "fp32" else TOL_BF16)
 
 
-@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 64, 48, 320, 320), (2, 32, 24, 192, 640), (1, 128, 96, 64, 128), (3, 24, 20, 192, 192),
-                                            (16, 32, 24, 640, 640)])
-def test_conv3x3_pair(cuda, n, h, w, cin, cout):
+@pytest.mark.parametrize("n,h,w,cin,cout,bn", [(2, 64, 48, 320, 320, 0), (2, 32, 24, 192, 640, 128), (1, 128, 96, 64, 128, 128),
+                                               (3, 24, 20, 192, 192, 192), (16, 32, 24, 640, 640, 0)])
+def test_conv3x3_pair(cuda, n, h, w, cin, cout, bn):
     from ladi_vton_b200 import ops, weights
     x = rnd((n, h, w, cin), cuda, 1).bfloat16()
     res = rnd((n, h, w, cout), cuda, 5).bfloat16()
     wt = rnd((cout, cin, 3, 3), cuda, 2, (9 * cin) ** -0.5)
     b = rnd((cout,), cuda, 3)
     wp = weights.pack_conv(wt, [cin])
-    y = ops.conv2d([x], wp, cout, bias=b, residual=res, pair=True, split_k=False)
-    y1 = ops.conv2d([x], wp, cout, bias=b, residual=res, pair=False, split_k=False)
+    y = ops.conv2d([x], wp, cout, bias=b, residual=res, pair=True, split_k=False, force_bn=bn)
+    y1 = ops.conv2d([x], wp, cout, bias=b, residual=res, pair=False, split_k=False, force_bn=bn)
     ref = conv_ref([x], wt, b) + res.float()
     torch.cuda.synchronize()
     assert nerr(y, ref) < TOL_BF16
@@ -418,11 +418,11 @@ def test_conv_pair_concat_shortcut_stride2(cuda):
     x1, x2 = rnd((n, h, w, c1), cuda, 1).bfloat16(), rnd((n, h, w, c2), cuda, 2).bfloat16()
     wt = rnd((cout, c1 + c2, 3, 3), cuda, 3, (9 * (c1 + c2)) ** -0.5)
     b = rnd((cout,), cuda, 4)
-    y = ops.conv2d([x1, x2], weights.pack_conv(wt, [c1, c2]), cout, bias=b, pair=True, split_k=False)
+    y = ops.conv2d([x1, x2], weights.pack_conv(wt, [c1, c2]), cout, bias=b, pair=True, split_k=False, force_bn=128)
     torch.cuda.synchronize()
     assert nerr(y, conv_ref([x1, x2], wt, b)) < TOL_BF16
     ws = rnd((cout, c1, 3, 3), cuda, 5, (9 * c1) ** -0.5)
-    y = ops.conv2d([x1], weights.pack_conv(ws, [c1]), cout, bias=b, stride=2, pair=True, split_k=False)
+    y = ops.conv2d([x1], weights.pack_conv(ws, [c1]), cout, bias=b, stride=2, pair=True, split_k=False, force_bn=128)
     torch.cuda.synchronize()
     assert nerr(y, conv_ref([x1], ws, b, stride=2)) < TOL_BF16
 

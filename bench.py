@@ -277,12 +277,13 @@ def main():
     t_conv, f_conv = sum(t for t, _ in conv), sum(f for _, f in conv)
     t_attn, f_attn = sum(t for t, _ in attn), sum(f for _, f in attn)
     ach = f_conv / (t_conv * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "convgemm_kernel (implicit-GEMM conv + linear, tcgen05)", "achieved": ach, "peak": sustained,
+    roofline = {"bound": "tensor", "kernel": "convgemm_kernel (implicit-GEMM conv + linear, tcgen05 cta_group::2 CTA pairs)", "achieved": ach, "peak": sustained,
                 "unit": "TFLOP/s", "frac": ach / sustained, "peak_source": src + ", sustained bf16",
-                "traffic": 23.18e6,
+                "traffic": 23.19e6,
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from ncu --set full "
-                                "(profiles/r01_ncu_top_kernels.txt): conv3x3 640->640 @32x24, batch 16, BN=256 -- 23.2 MB = inputs 15.7 + weights 7.4 read once; "
-                                "the 15.7 MB output is still L2-resident when the kernel ends (algorithmic bytes incl. the output write: 38.8 MB)",
+                                "(profiles/r01_ncu_pair_kernels.txt): conv3x3 640->640 @32x24, batch 16, BN=256, CTA pairs -- 23.2 MB = inputs 15.7 + "
+                                "weights 7.4 read once; the 15.7 MB output is still L2-resident when the kernel ends (algorithmic bytes incl. the output "
+                                "write: 38.8 MB); 85 % tensor-pipe active in that launch",
                 "launches_per_unet_forward": len(conv), "avg_launch_ms": t_conv / max(1, len(conv)),
                 "algorithmic_gflop_per_launch": f_conv / max(1, len(conv)) / 1e9, "share_of_unet_forward": t_conv / allk,
                 "attention": {"achieved": f_attn / (t_attn * 1e-3) / 1e12 if t_attn else None, "share_of_unet_forward": t_attn / allk,

@@ -162,6 +162,13 @@ LADI_API int ladi_ddim_cfg_step(const float* eps, int eps_pitch, float* latents,
                        int cfg, float guidance, const float* coef, int* step_ptr, int advance, void* stream);
 /* (x/2+0.5).clamp(0,1) NHWC bf16/fp32 [n,h,w,pitch] (first 3 channels) -> NHWC fp32 [n,h,w,3] (tryon_pipe.py:356-358). */
 LADI_API int ladi_image_out(const void* x, int x_is_fp32, int n, int h, int w, int x_pitch, float* out, void* stream);
+/* The same clamp followed by numpy_to_pil's (x * 255).round().astype(uint8) (DiffusionPipeline.numpy_to_pil, called at
+ * tryon_pipe.py:760; round-half-to-even like numpy): NHWC uint8 [n,h,w,3], so output_type="pil" moves a quarter of the bytes to the host. */
+LADI_API int ladi_image_out_u8(const void* x, int x_is_fp32, int n, int h, int w, int x_pitch, unsigned char* out, void* stream);
+/* ---- dataset tensorisation edge: src/utils/posemap.py:6-35 kpoint_to_heatmap for n_maps key-points
+ * (keypoints fp32 [n_maps,2] = (x, y) in pixels; the reference calls it per sample and joint with sigma 9, src/dataset/vitonhd.py:277-287):
+ * out fp32 [n_maps,h,w] = exp(-|p - k|^2 / sigma^2) / (max + eps), all zeros for a key-point with no coordinate > 0. */
+LADI_API int ladi_pose_heatmaps(const float* keypoints, int n_maps, int h, int w, float sigma, float* out, void* stream);
 
 /* ---- text / vision conditioning front-end (not on the per-step path) ------------------------------------
  * Exact softmax attention for short sequences and any head width that is a multiple of 8 (<= 128), optional causal mask:

@@ -539,6 +539,41 @@ __global__ void image_out_kernel(const void* __restrict__ x, int is_f32, int64_t
   }
 }
 
+// numpy_to_pil of the reference pipeline base class (called at tryon_pipe.py:760): (x * 255).round().astype(uint8) of the clamped
+// image, on the device -- the D2H copy shrinks 4x and the host only wraps the bytes in PIL images.  rintf = round-half-to-even = numpy.
+__global__ void image_out_u8_kernel(const void* __restrict__ x, int is_f32, int64_t npx, int x_pitch, uint8_t* __restrict__ out) {
+  ptx::pdl_wait();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npx * 3; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t px = i / 3;
+    const int ch = (int)(i % 3);
+    const float v = is_f32 ? reinterpret_cast<const float*>(x)[px * x_pitch + ch]
+                           : __bfloat162float(reinterpret_cast<const bf16*>(x)[px * x_pitch + ch]);
+    const float c = fminf(fmaxf(v * 0.5f + 0.5f, 0.f), 1.f);
+    out[i] = (uint8_t)rintf(c * 255.f);
+  }
+}
+
+// src/utils/posemap.py:6-35 kpoint_to_heatmap for all key-points of a batch: out[b,k,y,x] = exp(-((x-kx)^2 + (y-ky)^2) / sigma^2) / (max + eps)
+// when any coordinate of the key-point is > 0, else 0.  The maximum over the integer grid is attained at the grid point nearest to the
+// key-point (clamped into the map), so it has a closed form and the map is written in one pass.
+__global__ void pose_heatmap_kernel(const float* __restrict__ kpts, int n_maps, int h, int w, float inv_sigma2, float* __restrict__ out) {
+  ptx::pdl_wait();
+  const int64_t total = (int64_t)n_maps * h * w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w), y = (int)((i / w) % h);
+    const int m = (int)(i / ((int64_t)w * h));
+    const float kx = __ldg(kpts + 2 * m), ky = __ldg(kpts + 2 * m + 1);
+    float v = 0.f;
+    if (kx > 0.f || ky > 0.f) {
+      const float nx = fminf(fmaxf(rintf(kx), 0.f), (float)(w - 1)), ny = fminf(fmaxf(rintf(ky), 0.f), (float)(h - 1));
+      const float dmin = (nx - kx) * (nx - kx) + (ny - ky) * (ny - ky);
+      const float d = ((float)x - kx) * ((float)x - kx) + ((float)y - ky) * ((float)y - ky);
+      v = expf(-d * inv_sigma2) / (expf(-dmin * inv_sigma2) + 1.1920929e-07f);
+    }
+    out[i] = v;
+  }
+}
+
 inline int grid_for(int64_t total, int block = 256) {
   int64_t g = (total + block - 1) / block;
   const int64_t cap = (int64_t)ladi_num_sms() * 16;
@@ -679,6 +714,19 @@ extern "C" int ladi_ddim_cfg_step(const float* eps, int eps_pitch, float* latent
   LADI_CHECK(eps && latents && unet_in && coef, "ddim: null operand");
   LADI_CUDA(ladi_launch(ddim_cfg_kernel, dim3(grid_for((int64_t)B * 4 * h * w)), dim3(256), 0, STREAM, eps, eps_pitch, latents, (bf16*)unet_in, in_pitch, B, h * w, cfg,
                                                                          guidance, coef, step_ptr, advance));
+  return LADI_OK;
+}
+
+extern "C" int ladi_image_out_u8(const void* x, int x_is_fp32, int n, int h, int w, int x_pitch, unsigned char* out, void* stream) {
+  LADI_CHECK(x && out && n > 0 && h > 0 && w > 0 && x_pitch >= 3, "image_out_u8: bad extent");
+  LADI_CUDA(ladi_launch(image_out_u8_kernel, dim3(grid_for((int64_t)n * h * w * 3)), dim3(256), 0, STREAM, x, x_is_fp32, (int64_t)n * h * w, x_pitch, out));
+  return LADI_OK;
+}
+
+extern "C" int ladi_pose_heatmaps(const float* keypoints, int n_maps, int h, int w, float sigma, float* out, void* stream) {
+  LADI_CHECK(keypoints && out && n_maps > 0 && h > 0 && w > 0 && sigma > 0.f, "pose_heatmaps: bad extent");
+  LADI_CUDA(ladi_launch(pose_heatmap_kernel, dim3(grid_for((int64_t)n_maps * h * w)), dim3(256), 0, STREAM, keypoints, n_maps, h, w,
+                        1.f / (sigma * sigma), out));
   return LADI_OK;
 }
 

@@ -58,6 +58,8 @@ SIGNATURES = {
     "ladi_bilinear_down8": ([_P, _I, _I, _I, _I, _P, _P], _I),
     "ladi_ddim_cfg_step": ([_P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _I, _P], _I),
     "ladi_image_out": ([_P, _I, _I, _I, _I, _I, _P, _P], _I),
+    "ladi_image_out_u8": ([_P, _I, _I, _I, _I, _I, _P, _P], _I),
+    "ladi_pose_heatmaps": ([_P, _I, _I, _I, _F, _P, _P], _I),
     "ladi_attention_small": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _L, _L, _F, _I, _P], _I),
     "ladi_clip_embed": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
     "ladi_patchify": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], _I),

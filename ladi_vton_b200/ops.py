@@ -286,6 +286,23 @@ def image_out(x):
     return out
 
 
+def image_out_u8(x):
+    """(x/2+0.5).clamp(0,1) -> (v*255).round() as NHWC uint8 (numpy_to_pil's arithmetic on the device)."""
+    n, h, w, _ = x.shape
+    out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=x.device)
+    lib.call("ladi_image_out_u8", _ptr(x), int(x.dtype == torch.float32), n, h, w, x.stride(2), _ptr(out), _stream())
+    return out
+
+
+def pose_heatmaps(keypoints, h, w, sigma=9.0):
+    """src/utils/posemap.py kpoint_to_heatmap for a whole batch: keypoints fp32 [..., 2] (x, y) -> fp32 [..., h, w]."""
+    k = keypoints.to(torch.float32).contiguous()
+    assert k.shape[-1] == 2
+    out = torch.empty(tuple(k.shape[:-1]) + (h, w), dtype=torch.float32, device=k.device)
+    lib.call("ladi_pose_heatmaps", _ptr(k), k.numel() // 2, h, w, float(sigma), _ptr(out), _stream())
+    return out
+
+
 # ---- text / vision conditioning front-end (SURVEY.md 8(f) row 1) ---------------------------------------------------------------
 def attention_small(q, k, v, heads, scale, causal=False):
     """q [B, Nq, heads*hd], k/v [B, Nkv, heads*hd] bf16 views (last dim contiguous) -> [B, Nq, heads*hd] bf16.  Exact softmax,

@@ -294,6 +294,11 @@ class StableDiffusionTryOnePipeline:
                 callback(i, ts[i], s.latents)
         # 11. decode with the EMASC skips, clamp, D2H
         img = self.vae.decode_nhwc(s.latents, inter, self.emasc_int_layers if inter is not None else None, scale=1.0 / sf)
+        if output_type == "pil":  # numpy_to_pil's (x*255).round().astype(uint8) on the device: a quarter of the D2H bytes (:358-760)
+            from PIL import Image
+            u8 = ops.image_out_u8(img).cpu().numpy()
+            pil = [Image.fromarray(im) for im in u8]
+            return StableDiffusionPipelineOutput(images=pil, nsfw_content_detected=None) if return_dict else (pil, None)
         out = ops.image_out(img)  # [B, H, W, 3] fp32 in [0, 1]  (:356)
         if output_type == "pt":  # extension: leave the result on the device (used for device-resident timing / NCCL gather)
             return StableDiffusionPipelineOutput(images=out, nsfw_content_detected=None) if return_dict else (out, None)

@@ -180,3 +180,10 @@ def test_hub_constructors(tmp_path):
     assert isinstance(m, EMASC) and sum(v.numel() for v in sd.values()) == 7_965_696
     with pytest.raises(RuntimeError):  # wrong key set -> strict load fails like torch's load_state_dict
         hub.inversion_adapter("vitonhd", state_dict=sd)
+
+
+def test_coco_body25_mapping_known_answer():
+    """src/utils/posemap.py:37-58 (checked equal to the reference dict in the build container): 18 COCO joints, BODY_25 joint 8 skipped."""
+    from ladi_vton_b200.data import get_coco_body25_mapping
+    m = get_coco_body25_mapping()
+    assert len(m) == 18 and [m[i] for i in range(18)] == [0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18]

@@ -246,3 +246,17 @@ def test_s2d_weight_equals_strided_conv():
     x, w = torch.randn((2, 5, 8, 6), generator=g), torch.randn((7, 5, 4, 4), generator=g)
     xs = x.view(2, 5, 4, 2, 3, 2).permute(0, 3, 5, 1, 2, 4).reshape(2, 20, 4, 3)  # channel (sy*2+sx)*c + ch
     assert (F.conv2d(x, w, stride=2, padding=1) - F.conv2d(xs, s2d_weight(w), stride=1, padding=1)).abs().max() < 1e-4
+
+
+def test_posemap_oracle_matches_reference_golden():
+    """oracle/ladi_oracle/dataprep.py == the reference's own src/utils/posemap.py (golden written by tests/golden/make_posemap_golden.py
+    from the unmodified file): in-map, missing (no coordinate > 0), half-missing, off-map and tie key-points."""
+    import numpy as np
+    from ladi_oracle.dataprep import numpy_to_uint8, pose_heatmaps
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "posemap.npz"))
+    maps = pose_heatmaps(g["keypoints"], 64, 48, float(g["sigma"])).numpy()
+    assert maps.dtype == np.float32 and maps.shape == (20, 64, 48)
+    assert np.array_equal(maps, g["maps"])
+    assert float(maps[10].max()) == 0.0 and float(maps[11].max()) == 0.0 and float(maps[12].max()) > 0.99  # (0,0), (-3,-1) missing; (0,17.5) kept
+    x = np.array([[[[0.0, 0.5, 1.0], [0.00196, 0.00197, 0.49803922]]]], dtype=np.float32)
+    assert numpy_to_uint8(x).tolist() == [[[[0, 128, 255], [0, 1, 127]]]]  # 127.5 -> 128 and 127.00000110 -> 127: round half to even

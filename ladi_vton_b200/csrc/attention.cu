@@ -335,6 +335,9 @@ __device__ __forceinline__ void softmax_pair_lazy(const AttnParams& p, int n_til
     // maximum for the next reference
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     float x0 = -INFINITY, x1 = -INFINITY, x2 = -INFINITY, x3 = -INFINITY;
+    // (A variant with double-buffered 16-column TMEM reads -- next read in flight under the current exponentials -- measured SLOWER on
+    // B200: 351 vs 333 us at 3072 tokens, 2257 vs 2124 us at 12288, profiles/r01_attn_bench.jsonl; the two 32-column reads stay.)
+    {
 #pragma unroll
     for (int c = 0; c < COLS; c += 32) {
       uint32_t v[32], pk[16];
@@ -372,6 +375,7 @@ __device__ __forceinline__ void softmax_pair_lazy(const AttnParams& p, int n_til
       ptx::tmem_st16(tP + lane_off + half * (COLS / 2) + (c >> 1), pk);
       if (c == 0) TRACE(3);
       else TRACE(5);
+    }
     }
     l += (s0 + s1) + (s2 + s3);
     ptx::tmem_wait_st();

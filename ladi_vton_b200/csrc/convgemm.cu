@@ -714,9 +714,14 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
       if (d->act == 2 && kp.staged && cand[i] % 128 != 0) continue;  // GEGLU slabs consume 128 accumulator columns
       const long tiles = (long)kp.tiles_m * ((d->c_out + cand[i] - 1) / cand[i]);
       long cost = ((tiles + sms - 1) / sms) * (cand[i] + 64);
-      // short reductions (K <= 512) are epilogue-bound and the 32-column tail slab of a 160-wide tile is its slowest part:
-      // measured 35.8 us (BN=128) vs 40.0 us (BN=160) for the 49152x320x320 GEMMs, profiles/r01_bn_sweep.jsonl
-      if (total <= 8 && cand[i] % 64 != 0) cost += cost / 4;
+      if (total <= 8 && d->c_out >= 128) {
+        // short reductions (K <= 512) are epilogue-bound: the per-tile fixed cost is small, narrower tiles balance better and the
+        // 32-column tail slab of a 160-wide tile is its slowest part.  Measured for the 49152x320x320 GEMMs (profiles/r01_bn_sweep.jsonl):
+        // 35.8 us (BN=128), 40.0 (160), 39.9 (192), 48.1 (256); 49152x320x960: 54 us (192) vs 59.5 (128) / 62.5 (160).
+        if (cand[i] < 128) continue;
+        cost = ((tiles + sms - 1) / sms) * (cand[i] + 16);
+        if (cand[i] % 64 != 0) cost += cost / 4;
+      }
       if (best < 0 || cost < best) { best = cost; BN = cand[i]; }
     }
   }

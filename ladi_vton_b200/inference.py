@@ -264,6 +264,11 @@ def save_images(images, categories, names, save_dir, use_png):
     return paths
 
 
+def batches_for_rank(n_batches, rank, world):
+    """Which batch indices a rank processes: every world-th batch, like the sharded dataloader `accelerator.prepare` returns (:221)."""
+    return [i for i in range(n_batches) if i % world == rank]
+
+
 @torch.no_grad()
 def main(argv=None, models=None, dataset=None, size=(512, 384)):
     """`models=` / `dataset=` inject prebuilt engine objects / any dataset with the reference's batch keys (used by the tests)."""
@@ -299,8 +304,9 @@ def main(argv=None, models=None, dataset=None, size=(512, 384)):
         it = tqdm(test_dataloader, disable=rank != 0)
     except ImportError:
         it = test_dataloader
+    mine = set(batches_for_rank(len(test_dataloader), rank, world))
     for idx, batch in enumerate(it):
-        if idx % world != rank:
+        if idx not in mine:
             continue
         images = run_batch(batch, models, val_pipe, args, generator, device, processor=models.get("processor"), size=size)
         written += save_images(images, batch["category"], batch["im_name"], save_dir, args.use_png)

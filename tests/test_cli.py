@@ -129,3 +129,12 @@ def test_cli_has_no_cpu_path(tmp_path):
     with pytest.raises(RuntimeError, match="no CPU path"):
         main(["--output_dir", str(tmp_path), "--test_order", "paired", "--dataset", "vitonhd", "--synthetic_samples", "2", "--random_init"])
     assert os.listdir(tmp_path) == []
+
+
+def test_rank_sharding_covers_every_batch_once():
+    from ladi_vton_b200.inference import batches_for_rank
+    for n, world in ((7, 2), (8, 8), (3, 4), (0, 2), (10, 1)):
+        parts = [batches_for_rank(n, r, world) for r in range(world)]
+        assert sorted(i for p in parts for i in p) == list(range(n))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    assert batches_for_rank(7, 1, 2) == [1, 3, 5]

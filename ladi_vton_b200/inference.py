@@ -211,18 +211,24 @@ def _try_tokenizer(args):
     return CLIPTokenizer.from_pretrained(folder)
 
 
-def clip_pixel_values(cloth, device, processor=None):
+def clip_pixel_values(cloth, device, processor=None, mode="uint8"):
     """src/inference.py:265-268: resize((cloth + 1) / 2, (224, 224), antialias=True).clamp(0, 1) -> processor(...).pixel_values.
     With a `processor` object (the reference's `AutoProcessor`, when its files are available locally) the host path of the reference is
-    kept byte for byte; otherwise the resize, the clamp and the CLIP mean/std normalisation run as one kernel (ops.clip_preprocess)."""
+    kept byte for byte; otherwise the resize, the clamp and the CLIP normalisation run as one kernel (ops.clip_preprocess).  What
+    CLIPImageProcessor does to [0,1] floats is version behaviour (oracle/ladi_oracle/inference_body.py): `mode` = "uint8" (default, the
+    pinned transformers 4.27.3: floats round-trip through uint8), "double_rescale" ((v/255 - mean)/std, transformers >= 4.28 incl. the
+    installed 5.5) or "float" ((v - mean)/std)."""
     from . import ops
     if processor is not None:
         import torchvision
         x = torchvision.transforms.functional.resize((cloth + 1) / 2, (224, 224), antialias=True).clamp(0, 1)
         return processor(images=x, return_tensors="pt").pixel_values.to(device)
-    mean = torch.tensor(CLIP_MEAN, dtype=torch.float32, device=device)
-    std = torch.tensor(CLIP_STD, dtype=torch.float32, device=device)
-    return ops.clip_preprocess(cloth.to(device, torch.float32).contiguous(), 224, 224, mean, std)
+    if mode not in ("uint8", "double_rescale", "float"):
+        raise ValueError(f"unknown CLIP preprocessing mode {mode!r}")
+    k = 255.0 if mode == "double_rescale" else 1.0  # (v/255 - mean)/std == (v - 255 mean)/(255 std)
+    mean = torch.tensor(CLIP_MEAN, dtype=torch.float32, device=device) * k
+    std = torch.tensor(CLIP_STD, dtype=torch.float32, device=device) * k
+    return ops.clip_preprocess(cloth.to(device, torch.float32).contiguous(), 224, 224, mean, std, quantise=(mode == "uint8"))
 
 
 def prompts_for(categories, num_vstar):

@@ -6,11 +6,16 @@ adapter -> [B, num_vstar, D] pseudo-word embeddings (:276-277) -> prompt strings
 encode_text_word_embedding(...).last_hidden_state (:294-295) -> try-on pipeline (:298-311), where the '' prompt of classifier-free
 guidance is encoded through the same tokenizer + text encoder (tryon_pipe.py:284-301).
 
-The CLIP image processor of :267 (`AutoProcessor`, transformers 4.27.3, not installed here) is restated as its documented arithmetic for
-float input that is already 224x224 in [0,1]: per-channel (v - mean) / std with the `preprocessor_config.json` constants of
-laion/CLIP-ViT-H-14-laion2B-s32B-b79K.  **Parity unpinned** for that one step (no processor files / no transformers 4.27.3 in the
-container): whether 4.27.3 additionally round-trips the floats through uint8 is version behaviour that could not be checked; the engine
-exposes it as the `quantise` flag of ladi_clip_preprocess and the CLI accepts the real processor object when its files are local.
+The CLIP image processor of :267 (`AutoProcessor` -> CLIPImageProcessor, transformers 4.27.3, not installable here) receives float
+images that are already 224x224 in [0,1].  What it does to them is version behaviour, restated as three modes of `clip_pixel_values`:
+  * "uint8" (default): 4.27.3's `resize` round-trips every non-PIL image through PIL -- `to_pil_image` multiplies [0,1] floats by 255 and
+    truncates to uint8 -- and returns the uint8 array; `rescale(1/255)` and `normalize` follow: (floor(v*255)/255 - mean)/std.
+    [recalled from the 4.27 source; pinned here only through the installed library's identical uint8 branch, tests/test_oracle_pins.py]
+  * "double_rescale": later versions (and the installed 5.5, pinned in tests/test_oracle_pins.py) keep the float range through the
+    resize and then apply `rescale(1/255)` to the already-[0,1] image: (v/255 - mean)/std.
+  * "float": (v - mean)/std, no quantisation.
+mean/std = `preprocessor_config.json` of laion/CLIP-ViT-H-14-laion2B-s32B-b79K.  The CLI takes the real processor object when its files
+are local, which settles the question for a given installation.
 """
 import torch
 import torch.nn.functional as F
@@ -23,13 +28,17 @@ CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 CATEGORY_TEXT = {'dresses': 'a dress', 'upper_body': 'an upper body garment', 'lower_body': 'a lower body garment'}  # :279-283
 
 
-def clip_pixel_values(cloth, quantise=False):
+def clip_pixel_values(cloth, mode="uint8"):
     """src/inference.py:265-268."""
     x = F.interpolate((cloth.float() + 1) / 2, size=(224, 224), mode="bilinear", antialias=True, align_corners=False).clamp(0, 1)
-    if quantise:
-        x = torch.floor(x * 255) / 255
     mean = torch.tensor(CLIP_MEAN).view(1, 3, 1, 1)
     std = torch.tensor(CLIP_STD).view(1, 3, 1, 1)
+    if mode == "uint8":
+        x = torch.floor(x * 255) / 255
+    elif mode == "double_rescale":
+        x = x / 255
+    elif mode != "float":
+        raise ValueError(mode)
     return (x - mean) / std
 
 

@@ -24,7 +24,7 @@ def test_clip_preprocess(cuda, quantise):
     from ladi_oracle.inference_body import CLIP_MEAN, CLIP_STD, clip_pixel_values
     from ladi_vton_b200 import ops, synthetic as S
     cloth = S.warp_inputs(2, 512, 384, seed=3)["cloth"] * 1.2  # exceeds [-1,1] in places: exercises the clamp
-    ref = clip_pixel_values(cloth, quantise)
+    ref = clip_pixel_values(cloth, "uint8" if quantise else "float")
     mean, std = torch.tensor(CLIP_MEAN, device=cuda), torch.tensor(CLIP_STD, device=cuda)
     out = ops.clip_preprocess(cloth.to(cuda).contiguous(), 224, 224, mean, std, quantise).cpu()
     assert out.shape == ref.shape == (2, 3, 224, 224)

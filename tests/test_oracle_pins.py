@@ -260,3 +260,26 @@ def test_posemap_oracle_matches_reference_golden():
     assert float(maps[10].max()) == 0.0 and float(maps[11].max()) == 0.0 and float(maps[12].max()) > 0.99  # (0,0), (-3,-1) missing; (0,17.5) kept
     x = np.array([[[[0.0, 0.5, 1.0], [0.00196, 0.00197, 0.49803922]]]], dtype=np.float32)
     assert numpy_to_uint8(x).tolist() == [[[[0, 128, 255], [0, 1, 127]]]]  # 127.5 -> 128 and 127.00000110 -> 127: round half to even
+
+
+def test_clip_pixel_values_modes_pinned_to_installed_processor():
+    """src/inference.py:265-268.  The installed transformers' CLIPImageProcessor (laion ViT-H preprocessor constants) pins two of the
+    oracle's modes: [0,1] float input -> "double_rescale" (what versions >= 4.28 do), uint8 input -> "uint8" (the branch transformers
+    4.27.3 reaches for float input, because its resize round-trips through PIL uint8)."""
+    from transformers import CLIPImageProcessor
+    from ladi_oracle.inference_body import CLIP_MEAN, CLIP_STD, clip_pixel_values
+    proc = CLIPImageProcessor(do_resize=True, size={"shortest_edge": 224}, do_center_crop=True, crop_size={"height": 224, "width": 224},
+                              do_rescale=True, rescale_factor=1 / 255, do_normalize=True, image_mean=list(CLIP_MEAN), image_std=list(CLIP_STD),
+                              resample=3)
+    g = torch.Generator().manual_seed(4)
+    cloth = torch.rand((2, 3, 256, 192), generator=g) * 2.4 - 1.2  # exceeds [-1, 1]: the clamp matters
+    x01 = torch.nn.functional.interpolate((cloth + 1) / 2, size=(224, 224), mode="bilinear", antialias=True).clamp(0, 1)
+    lib_float = proc(images=x01, return_tensors="pt").pixel_values
+    assert float((clip_pixel_values(cloth, "double_rescale") - lib_float).abs().max()) < 1e-6
+    u8 = torch.floor(x01 * 255).to(torch.uint8)
+    lib_u8 = proc(images=u8, return_tensors="pt").pixel_values
+    assert float((clip_pixel_values(cloth, "uint8") - lib_u8).abs().max()) < 1e-5
+    d = (clip_pixel_values(cloth, "uint8") - clip_pixel_values(cloth, "float")).abs().max()
+    assert 0 < float(d) <= 1 / 255 / min(CLIP_STD) + 1e-6
+    with pytest.raises(ValueError):
+        clip_pixel_values(cloth, "nope")

@@ -215,7 +215,7 @@ def clip_pixel_values(cloth, device, processor=None, mode="uint8"):
     """src/inference.py:265-268: resize((cloth + 1) / 2, (224, 224), antialias=True).clamp(0, 1) -> processor(...).pixel_values.
     With a `processor` object (the reference's `AutoProcessor`, when its files are available locally) the host path of the reference is
     kept byte for byte; otherwise the resize, the clamp and the CLIP normalisation run as one kernel (ops.clip_preprocess).  What
-    CLIPImageProcessor does to [0,1] floats is version behaviour (oracle/ladi_oracle/inference_body.py): `mode` = "uint8" (default, the
+    CLIPImageProcessor does to [0,1] floats is version behaviour: `mode` = "uint8" (default, the
     pinned transformers 4.27.3: floats round-trip through uint8), "double_rescale" ((v/255 - mean)/std, transformers >= 4.28 incl. the
     installed 5.5) or "float" ((v - mean)/std)."""
     from . import ops

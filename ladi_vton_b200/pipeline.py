@@ -12,7 +12,6 @@ import inspect
 from dataclasses import dataclass
 from typing import Any
 
-import numpy as np
 import torch
 
 from . import lib, ops

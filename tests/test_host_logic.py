@@ -4,7 +4,6 @@ and the N>1 sharding logic over a world_size-2 gloo group."""
 import os
 import re
 import subprocess
-import sys
 
 import pytest
 import torch

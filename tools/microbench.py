@@ -42,7 +42,6 @@ for n, hw, c0, c1 in [(16, 3072, 320, 0), (16, 3072, 640, 320), (16, 768, 640, 0
     out = torch.empty((n, h, w, C), dtype=torch.bfloat16, device=dev)
     srcs = [x0] + ([x1] if c1 else [])
     wsb = ws.get(n, hw, 32)
-    import ctypes as Cc
     from ladi_vton_b200 import lib
     P = ops._ptr
     s = ops._stream()

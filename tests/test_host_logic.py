@@ -186,3 +186,36 @@ def test_coco_body25_mapping_known_answer():
     from ladi_vton_b200.data import get_coco_body25_mapping
     m = get_coco_body25_mapping()
     assert len(m) == 18 and [m[i] for i in range(18)] == [0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18]
+
+
+def test_bench_algorithmic_flops_known_answers():
+    """bench.py's per-image algorithmic work = SURVEY.md 8(d) / Appendix C (2 flops per MAC of convs, linears, QK^T, PV only):
+    15.61 / 33.06 / 62.15 / 120.32 TFLOP at 512x384 for (N, CFG) = (20, off), (50, off), (50, on), (100, on); 79.43 / 173.68 / 330.77 / 644.93
+    at 1024x768."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    want = {(512, 384): (15.61, 33.06, 62.15, 120.32), (1024, 768): (79.43, 173.68, 330.77, 644.93)}
+    for (h, w), vals in want.items():
+        got = (bench.tflop_per_image(h, w, 20, False), bench.tflop_per_image(h, w, 50, False), bench.tflop_per_image(h, w, 50, True),
+               bench.tflop_per_image(h, w, 100, True))
+        for g, v in zip(got, vals):
+            assert abs(g - v) < 0.01, (h, w, got, vals)
+    assert bench.tflop_per_image(256, 192, 50, True) < bench.tflop_per_image(512, 384, 50, True)  # other sizes: area-scaled estimate
+
+
+def test_synthetic_workload_matches_survey_spec():
+    """image / cloth ~ U(-1,1), binary centred-rectangle mask over ~35 % of the pixels, 18 Gaussian pose maps (sigma 9,
+    exp(-r^2/81)) in [0,1], N(0,1) prompt embeddings [B,77,1024]; seeded (CLI default 1234) and deterministic."""
+    from ladi_vton_b200 import synthetic as S
+    a, b = S.synthetic_inputs(2, 512, 384), S.synthetic_inputs(2, 512, 384)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert a["image"].shape == a["warped_cloth"].shape == (2, 3, 512, 384) and float(a["image"].min()) >= -1 and float(a["image"].max()) <= 1
+    m = a["mask_image"]
+    assert m.shape == (2, 1, 512, 384) and set(m.unique().tolist()) == {0.0, 1.0} and 0.33 < float(m.mean()) < 0.37
+    p = a["pose_map"]
+    assert p.shape == (2, 18, 512, 384) and float(p.min()) >= 0 and 0.5 < float(p.amax(dim=(2, 3)).min()) <= 1.0
+    assert a["prompt_embeds"].shape == a["negative_prompt_embeds"].shape == (2, 77, 1024)
+    assert abs(float(a["prompt_embeds"].std()) - 1.0) < 0.02
+    assert not torch.equal(S.synthetic_inputs(2, 512, 384, seed=1)["image"], a["image"])

@@ -94,23 +94,9 @@ def cpu_reference_sample(args):
     from ladi_vton_b200 import synthetic as S
     from ladi_vton_b200.unet import unet_param_shapes
     from ladi_vton_b200.vae import vae_param_shapes
-    # thread count: "all the host threads it can use" -- on many-core hosts PyTorch's CPU kernels get SLOWER past a point
-    # (sync overhead on these layer sizes), so calibrate on a representative conv + GEMM and keep the fastest setting
-    import torch.nn.functional as Fc
-    cands = sorted({c for c in (os.cpu_count(), os.cpu_count() // 2, os.cpu_count() // 4, 32, 16) if c and 1 <= c <= os.cpu_count()}, reverse=True)
-    xc, wc = torch.randn(2, 320, 64, 48), torch.randn(320, 320, 3, 3)
-    ac, bc = torch.randn(6144, 320), torch.randn(1280, 320)
-    best, best_t = cands[0], None
-    with torch.no_grad():
-        for c in cands:
-            torch.set_num_threads(c)
-            Fc.conv2d(xc, wc, padding=1); ac @ bc.t()
-            t0 = time.perf_counter()
-            for _ in range(3):
-                Fc.conv2d(xc, wc, padding=1); ac @ bc.t(); Fc.layer_norm(ac, (320,))
-            dt = time.perf_counter() - t0
-            if best_t is None or dt < best_t:
-                best, best_t = c, dt
+    # thread count: PINNED to min(64, host threads).  On these layer sizes PyTorch's CPU kernels get slower past ~64 threads (sync
+    # overhead; measured in round 1 on the 128-thread GPU-box hosts), and a per-run calibration made the arm swing 6x between runs.
+    best = max(1, min(64, os.cpu_count() or 1))
     torch.set_num_threads(best)
     args.cpu_threads = best
     cfg = args.guidance > 1.0
@@ -167,10 +153,13 @@ def run_reference(args, rank):
     cores = getattr(args, "cpu_threads", os.cpu_count())
     line = {"metric": "try-on images/sec", "value": v, "unit": "images/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall / args.steps_done * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "steps_completed": args.steps_done, "warmup_completed": args.warmup_done, "dtype": "fp32", "data": "synthetic", "config": workload_config(args),
+            "steps_completed": args.steps_done, "warmup_completed": args.warmup_done, "dtype": "fp32", "data": "synthetic",
+            "config": dict(workload_config(args), reference_sample=f"what this arm actually executes: batch 1 (UNet batch {2 if args.guidance > 1 else 1}), fp32, "
+                           f"ONE UNet forward + one image through VAE enc x2 / EMASC / dec per step, images/s extrapolated to {args.ddim_steps} DDIM steps; "
+                           f"{cores} host threads (pinned)"),
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                              "sample": f"1 UNet fwd (batch {2 if args.guidance > 1 else 1}) {tu:.2f}s + 1 image VAE enc x2/EMASC/dec {tv:.2f}s per step; "
-                                       f"extrapolated to {args.ddim_steps} DDIM steps; torch {torch.__version__} fp32, {cores} of {os.cpu_count()} host threads (fastest calibrated setting)"},
+                                       f"extrapolated to {args.ddim_steps} DDIM steps; torch {torch.__version__} fp32, {cores} of {os.cpu_count()} host threads (pinned: min(64, host threads))"},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -180,7 +169,7 @@ def workload_config(args):
     return {"workload": f"VITON-HD shape {args.height}x{args.width}, batch {args.batch}/GPU, {args.ddim_steps} DDIM steps, "
                         f"guidance_scale {args.guidance} ({'CFG on: UNet batch ' + str(2 * args.batch) if cfg else 'no CFG'}), bf16, CUDA-graph denoise loop",
             "global_batch": args.batch * args.gpus, "height": args.height, "width": args.width, "ddim_steps": args.ddim_steps,
-            "guidance_scale": args.guidance, "parallelism": f"dp{args.gpus} (batch-sharded replicas, NCCL all_gather of the images)",
+            "guidance_scale": args.guidance, "parallelism": f"dp{args.gpus} (batch-sharded replicas, NCCL all_gather of the uint8 images)",
             "l2": "working set (1.9 GB bf16 weights per UNet forward) >> 126 MB L2; no flush needed"}
 
 
@@ -217,7 +206,8 @@ def main():
     pinned = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
     gen = torch.Generator(device=dev).manual_seed(1234)
-    gather = torch.empty((world * B, H, W, 3), dtype=torch.float32, device=dev) if world > 1 else None
+    gather = torch.empty((world * B, H, W, 3), dtype=torch.uint8, device=dev) if world > 1 else None  # numpy_to_pil's uint8, 0.59 MB / image
+    host_all = torch.empty((world * B, H, W, 3), dtype=torch.uint8, pin_memory=True) if (world > 1 and rank == 0) else None
 
     def call(inputs, output_type):
         out = pipe(image=inputs["image"], mask_image=inputs["mask_image"], pose_map=inputs["pose_map"], warped_cloth=inputs["warped_cloth"],
@@ -226,17 +216,21 @@ def main():
         return out
 
     def step_resident():
-        img = call(resident, "pt")
+        img = call(resident, "pt_u8" if world > 1 else "pt")
         if world > 1:
             dist.all_gather_into_tensor(gather, img)  # the path's only collective: final image gather over NVLink
 
     def step_e2e():
         dev_in = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}  # H2D from pinned host memory
-        if world > 1:
-            img = call(dev_in, "pt")
+        if world > 1:  # every rank: H2D of its shard -> pipeline -> uint8 gather; rank 0: D2H of the whole batch into pinned memory
+            img = call(dev_in, "pt_u8")
             dist.all_gather_into_tensor(gather, img)
-            return (gather if rank == 0 else img).cpu().numpy()
-        return call(dev_in, "np")  # D2H inside
+            if rank == 0:
+                host_all.copy_(gather, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return host_all.numpy()
+            return None
+        return call(dev_in, "np")  # D2H (pinned staging) inside
 
     def timed(fn, warmup, steps):
         for _ in range(warmup):
@@ -267,7 +261,8 @@ def main():
     # ---- roofline of the dominant kernel: one instrumented eager UNet forward, every conv/GEMM launch bracketed by CUDA events
     sustained, burst, hbm, src = peaks()
     ops.PROFILE = []
-    s = pipe._sessions[(B, 2 * B if cfg else B, H // 8, W // 8)]
+    s = next(iter(pipe._sessions.values()))
+    pipe.unet._ctx = s.ctx_kv
     pipe.unet.forward_nhwc(s.unet_in, s.step)
     torch.cuda.synchronize()
     conv = [(e0.elapsed_time(e1), fl) for (name, e0, e1, fl, _) in ops.PROFILE if name == "ladi_conv2d_bf16"]
@@ -277,17 +272,62 @@ def main():
     t_conv, f_conv = sum(t for t, _ in conv), sum(f for _, f in conv)
     t_attn, f_attn = sum(t for t, _ in attn), sum(f for _, f in attn)
     ach = f_conv / (t_conv * 1e-3) / 1e12
+    # the same launches INSIDE the replayed step graph (what the timed region runs): kernel durations from one CUPTI-traced replay
+    # (torch.profiler), outside the timed region.  Reported beside the event-bracketed eager figure, never instead of it.
+    in_graph = None
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        s.step.zero_()
+        s.g_step.replay(); torch.cuda.synchronize()
+        s.step.zero_()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            s.g_step.replay()
+            torch.cuda.synchronize()
+        ev = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "Memcpy" not in e.name and "Memset" not in e.name),
+                    key=lambda e: e.time_range.start)
+        # exclusive time per kernel: with programmatic dependent launch a kernel's CTAs start (and wait) while its predecessor drains;
+        # only the part after the predecessor's end is attributed to it, so the family sums add up to the step's wall time
+        fam = {"conv": 0.0, "attention": 0.0, "norm": 0.0, "other": 0.0}
+        prev_end = None
+        for e in ev:
+            st = e.time_range.start if prev_end is None else max(e.time_range.start, prev_end)
+            d = max(0.0, e.time_range.end - st) * 1e-3  # ms
+            k = ("conv" if ("convgemm_kernel" in e.name or "splitk_reduce" in e.name) else "attention" if "attention_" in e.name
+                 else "norm" if ("gn_" in e.name or "layernorm" in e.name) else "other")
+            fam[k] += d
+            prev_end = e.time_range.end if prev_end is None else max(prev_end, e.time_range.end)
+        wall = (prev_end - ev[0].time_range.start) * 1e-3
+        in_graph = {"conv_ms": fam["conv"], "attention_ms": fam["attention"], "norm_ms": fam["norm"], "other_ms": fam["other"], "kernels": len(ev),
+                    "step_wall_ms": wall, "conv_tflops": f_conv / (fam["conv"] * 1e-3) / 1e12 if fam["conv"] else None,
+                    "attention_tflops": f_attn / (fam["attention"] * 1e-3) / 1e12 if fam["attention"] else None,
+                    "unet_forward_tflops": (f_conv + f_attn) / (wall * 1e-3) / 1e12}
+    except Exception as e:  # the profiler is evidence, not the product: never fail the bench on it
+        in_graph = {"error": repr(e)[:200]}
     roofline = {"bound": "tensor", "kernel": "convgemm_kernel (implicit-GEMM conv + linear, tcgen05 cta_group::2 CTA pairs)", "achieved": ach, "peak": sustained,
                 "unit": "TFLOP/s", "frac": ach / sustained, "peak_source": src + ", sustained bf16",
-                "traffic": 23.19e6,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel from ncu --set full "
-                                "(profiles/r01_ncu_pair_kernels.txt): conv3x3 640->640 @32x24, batch 16, BN=256, CTA pairs -- 23.2 MB = inputs 15.7 + "
-                                "weights 7.4 read once; the 15.7 MB output is still L2-resident when the kernel ends (algorithmic bytes incl. the output "
-                                "write: 38.8 MB); 85 % tensor-pipe active in that launch",
+                "how": "achieved = sum of algorithmic 2*M*N*K over the conv/GEMM launches of ONE UNet forward / sum of their CUDA-event durations, "
+                       "each launch bracketed on torch's current stream in an eager (un-graphed) forward after the timed region; "
+                       "in_graph = the same launches inside the replayed step graph, durations from a CUPTI trace of one replay",
+                "in_graph": in_graph, "frac_in_graph": (in_graph["conv_tflops"] / sustained) if in_graph and in_graph.get("conv_tflops") else None,
+                "traffic": None, "traffic_note": None,
                 "launches_per_unet_forward": len(conv), "avg_launch_ms": t_conv / max(1, len(conv)),
-                "algorithmic_gflop_per_launch": f_conv / max(1, len(conv)) / 1e9, "share_of_unet_forward": t_conv / allk,
-                "attention": {"achieved": f_attn / (t_attn * 1e-3) / 1e12 if t_attn else None, "share_of_unet_forward": t_attn / allk,
-                              "launches": len(attn)}}
+                "algorithmic_gflop_per_launch": f_conv / max(1, len(conv)) / 1e9, "share_of_unet_forward": t_conv / allk}
+    # per-launch DRAM traffic of the dominant kernel: only from a COMMITTED ncu capture of this very workload (profiles/r02_ncu_traffic.json,
+    # written by tools/ncu_traffic.py from `ncu --set full`), matched on the workload key; otherwise null -- never a constant from another run
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("workload_key") == [B, H, W, bool(cfg)]:
+            roofline["traffic"] = tj["avg_dram_bytes_per_launch"]
+            roofline["traffic_note"] = tj["note"]
+    except Exception:
+        pass
+    attention_roofline = {"bound": "tensor (MUFU-limited softmax at head_dim 64)", "kernel": "attention_pair_kernel / attention_single_kernel (flash, tcgen05 + TMEM)",
+                          "achieved": f_attn / (t_attn * 1e-3) / 1e12 if t_attn else None, "peak": sustained, "unit": "TFLOP/s",
+                          "frac": (f_attn / (t_attn * 1e-3) / 1e12 / sustained) if t_attn else None,
+                          "achieved_in_graph": in_graph.get("attention_tflops") if in_graph else None,
+                          "share_of_unet_forward": t_attn / allk, "launches": len(attn),
+                          "algorithmic_gflop_per_forward": f_attn / 1e9}
 
     if rank == 0:
         imgs = B * world
@@ -298,9 +338,10 @@ def main():
         line = {"metric": "try-on images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": workload_config(args), "clocks": clocks, "gpu_launches": launches,
-                "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * (world if world > 1 else 1) * H * W * 3 * 4,
+                "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": (B * world * H * W * 3) if world > 1 else (B * H * W * 3 * 4),  # N>1: rank 0 reads the gathered uint8 batch; N=1: fp32 numpy
                         "ms_per_step": ms_e2e},
-                "roofline": roofline,
+                "roofline": roofline, "roofline_attention": attention_roofline,
                 "pipeline_tensor_frac": value * tf_img / (sustained * world), "tflop_per_image": tf_img}
         if world == 1 and not args.no_cpu_baseline:
             sample = cpu_reference_sample(args)

@@ -88,6 +88,20 @@ typedef struct ladi_conv_desc {
   int pair_mode;             /* CTA pairs (tcgen05 cta_group::2, M = 256 across the two SMs of a TPC, each staging half of B):
                                 0 = library default (pairs when the shape allows; env LADI_CONV_2CTA=0 disables), 1 = force (error if the shape
                                 cannot pair), 2 = never */
+  /* LayerNorm folded into the GEMMs on either side of it (BasicTransformerBlock.norm1/2/3 of the UNet, call-site tryon_pipe.py:732):
+   * the PRODUCER of the normalised tensor also writes, per output row and 32-column chunk, {sum, sum of squares} of what it stores
+   * (rowstat_out: fp32 [rows][c_out/32][2]); the CONSUMER multiplies the RAW tensor with W' = W diag(gamma) and corrects in its epilogue:
+   * out[r,c] = rstd_r * (acc[r,c] - mean_r * ln_colsum[c]) + bias[c], bias = W beta (+ the linear's own bias); the LayerNorm pass and its
+   * HBM round trip disappear.  ln_stats is the producer's rowstat_out for this GEMM's A rows (normalised width = src_c[0], %% 64 == 0). */
+  float* rowstat_out;
+  const float* ln_stats;
+  const float* ln_colsum;    /* fp32 [c_out]: row sums of the bf16 weight actually multiplied */
+  float ln_eps;
+  /* nearest-2x upsample fused into the 3x3 convolution that follows it (diffusers Upsample2D: F.interpolate(scale_factor=2) + conv;
+   * UNet up blocks and VAE decoder vae.py:142-174): src = the HALF-resolution tensor [n, h_out/2, w_out/2, C]; each output parity
+   * (y&1, x&1) is a 2x2-tap convolution of it with merged weights (weights.pack_conv_up2x: [4 parities * c_out][4 taps * Cpad]),
+   * 4/9 of the multiply-adds of the materialised form and no intermediate tensor.  ksize 3, stride 1, bf16 output. */
+  int up2x;
 } ladi_conv_desc;
 LADI_API int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream);
 
@@ -104,8 +118,13 @@ typedef struct ladi_attn_desc {
   float scale;               /* softmax(scale * q k^T) */
   int variant;               /* 0 = auto; 1 = one query tile per CTA; 2 = two query tiles per CTA (tests / tuning) */
   void* trace;               /* optional device int64[8192]: per-phase clock64() stamps of CTA (0,0,0) (tools/attn_trace.py); NULL */
+  int head_dim;              /* ladi_attention_d512_bf16 only: 0 or 512 (the VAE), or 256 (reduced-width test models) */
 } ladi_attn_desc;
 LADI_API int ladi_attention_bf16(const ladi_attn_desc* d, void* stream);
+/* The same for ONE head of width 512: the VAE mid-block AttentionBlock (src/models/vae.py:81-90,112 encoder; :142-150,187 decoder;
+ * N = h*w tokens: 3072 at 512x384, 12288 at 1024x768).  heads must be 1, pitches >= head_dim; `variant` / `trace` ignored.  Flash-style:
+ * the N x N score matrix is never written (the reference's baddbmm + softmax + bmm materialises it per sample). */
+LADI_API int ladi_attention_d512_bf16(const ladi_attn_desc* d, void* stream);
 
 /* ---- normalisation ---------------------------------------------------------------------------------------------------
  * GroupNorm(+SiLU) over the channel-concat of up to two NHWC sources (diffusers ResnetBlock2D.norm1/norm2,
@@ -156,10 +175,15 @@ LADI_API int ladi_bilinear_down8(const float* x, int n, int c, int H, int W, flo
 /* One DDIM step with classifier-free guidance and re-assembly of the next UNet input (tryon_pipe.py:715,735-741 +
  * DDIMScheduler.step): eps NHWC fp32 [cfg?2B:B, h, w, eps_pitch] (first 4 channels), latents NCHW fp32 [B,4,h,w] updated
  * in place; unet_in NHWC bf16 [cfg?2B:B, h, w, in_pitch] channels 0..3 rewritten for both halves.  coef = device table
- * [steps][4] = {1/sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev)}, indexed by *step_ptr, which is then incremented
- * by the last block when advance != 0. */
+ * [steps][8] = {1/sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev-sigma_t^2), sigma_t, 0, 0, 0}, indexed by *step_ptr, which is
+ * then incremented by the last block when advance != 0.  noise: NCHW fp32 [B,4,h,w] variance noise of the eta > 0 (stochastic)
+ * DDIM update, x_prev += sigma_t * noise; NULL for eta = 0. */
 LADI_API int ladi_ddim_cfg_step(const float* eps, int eps_pitch, float* latents, void* unet_in, int in_pitch, int B, int h, int w,
-                       int cfg, float guidance, const float* coef, int* step_ptr, int advance, void* stream);
+                       int cfg, float guidance, const float* coef, int* step_ptr, int advance, const float* noise, void* stream);
+/* diffusers prepare_mask_and_masked_image, tensor branch (called at tryon_pipe.py:630), without host synchronisation: range checks
+ * image in [-1,1] / mask in [0,1] recorded in flags[0] / flags[1] (device int32[2], OR-ed; the pipeline reads them once, with the result)
+ * and the IN-PLACE binarisation of the caller's mask at 0.5.  image fp32 [n_image], mask fp32 [n_mask], both dense. */
+LADI_API int ladi_check_binarise(const float* image, long long n_image, float* mask, long long n_mask, int* flags, void* stream);
 /* (x/2+0.5).clamp(0,1) NHWC bf16/fp32 [n,h,w,pitch] (first 3 channels) -> NHWC fp32 [n,h,w,3] (tryon_pipe.py:356-358). */
 LADI_API int ladi_image_out(const void* x, int x_is_fp32, int n, int h, int w, int x_pitch, float* out, void* stream);
 /* The same clamp followed by numpy_to_pil's (x * 255).round().astype(uint8) (DiffusionPipeline.numpy_to_pil, called at

@@ -698,6 +698,265 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
 }
 
+
+// ============================================================================================ one head, head_dim 512
+// VAE mid-block AttentionBlock (/root/reference/src/models/vae.py:81-90,112 encoder; :142-150,187 decoder; diffusers 0.14
+// AttentionBlock: 1 head, d = C = 512, N = h*w tokens -- 3072 at 512x384, 12288 at 1024x768).  Flash-style: the N x N score matrix
+// never exists.  One CTA = one 128-row query tile x ONE HALF of the value/output width (blockIdx.y), because the fp32 accumulators of
+// a full 128 x 512 output tile would fill all 512 tensor-memory columns by themselves:
+//   TMEM  [0,128) S buffer 0   [128,256) S buffer 1   [256,512) O (128 x 256 fp32);  P(j) (bf16) overwrites S(j) in place;
+//   SMEM  Q tile resident as 8 K-chunks [128 x 64] (128 KiB) + a ring of 16-KiB stages through which BOTH operands stream:
+//         the 8 d-chunks [128 keys x 64] of K tile j (S += Q_c K_c^T), then the 4 column chunks [128 keys x 64] of V tile j
+//         (O[:, 64c..] += P V_c, V read MN-major straight from the TMA tile);
+//   issue order on the tensor pipe: QK(0), QK(1), PV(0), QK(2), PV(1), ...  so the softmax of tile j (MUFU floor ~1024 clk for
+//         128 x 128 exponentials) runs under QK(j+1) (2048 clk) and the pipe never waits for it.
+// The half split recomputes S once per half (1.5x the tensor work of an ideal kernel); d = 512 makes the kernel MMA-bound
+// (3072 tensor clk vs ~1600 softmax clk per KV tile), unlike the d = 64 kernels above.
+// Templated on the head width D in {512, 256}: 256 (the reduced-width test models) needs no value split (O = 256 columns).
+constexpr int D5_VHALF = 256, D5_VCHUNKS = D5_VHALF / 64;
+constexpr int D5_STAGES = 5;
+
+template <int D5>
+__global__ void __launch_bounds__(384, 1)
+attention_d512_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int D5_CHUNKS = D5 / 64;
+  uint8_t* sQ = smem;                                   // D/64 chunks [128 rows][64 d]
+  uint8_t* sR = sQ + D5_CHUNKS * TILE_BYTES;            // operand ring
+  float* xm = reinterpret_cast<float*>(sR + D5_STAGES * TILE_BYTES);  // row-max / row-sum exchange [parity][half][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xm + 2 * 256);
+  const uint32_t b0 = ptx::smem_u32(bars);
+  const uint32_t q_full = b0, full0 = b0 + 8, empty0 = full0 + 8 * D5_STAGES, s_full0 = empty0 + 8 * D5_STAGES, p_full0 = s_full0 + 16,
+                 o_ready = p_full0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1 + 2 * D5_STAGES + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, vh = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = p.n_kv_tiles;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < D5_STAGES; ++s) {
+      ptx::mbar_init(full0 + 8 * s, 1);
+      ptx::mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(s_full0 + 8 * s, 1);
+      ptx::mbar_init(p_full0 + 8 * s, 256);
+    }
+    ptx::mbar_init(o_ready, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tO = tmem_base + 256;
+  ptx::pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer: Q once, then the K / V chunk stream in the
+    // exact order the MMA issuer consumes it: K(0), K(1), V(0), K(2), V(1), ..., K(n-1), V(n-2), V(n-1)
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(q_full, D5_CHUNKS * TILE_BYTES);
+      for (int c = 0; c < D5_CHUNKS; ++c) ptx::tma_load_3d(&tmQ, ptx::smem_u32(sQ + c * TILE_BYTES), q_full, c * 64, qt * BQ, b);
+    }
+    __syncwarp();
+    uint32_t stage = 0, phase = 0;
+    auto load_chunks = [&](const CUtensorMap* tm, int col0, int nchunks, int tile) {
+      for (int c = 0; c < nchunks; ++c) {
+        ptx::mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        const uint32_t fb = full0 + 8 * stage;
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(fb, TILE_BYTES);
+          ptx::tma_load_3d(tm, ptx::smem_u32(sR + stage * TILE_BYTES), fb, col0 + c * 64, tile * BKV, b);
+        }
+        __syncwarp();
+        if (++stage == D5_STAGES) { stage = 0; phase ^= 1; }
+      }
+    };
+    load_chunks(&tmK, 0, D5_CHUNKS, 0);
+    for (int j = 0; j < n_tiles; ++j) {
+      if (j + 1 < n_tiles) load_chunks(&tmK, 0, D5_CHUNKS, j + 1);
+      load_chunks(&tmV, vh * D5_VHALF, D5_VCHUNKS, j);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, one elected lane issues)
+    constexpr uint32_t idesc_qk = ptx::idesc_bf16(128, BKV, 0, 0);
+    constexpr uint32_t idesc_pv = ptx::idesc_bf16(128, 64, 0, 1);  // A = P from tensor memory, B = V chunk, MN-major
+    const uint64_t q0 = ptx::smem_desc_sw128(ptx::smem_u32(sQ));
+    constexpr uint64_t CHUNK_DESC = TILE_BYTES >> 4;
+    uint32_t stage = 0, phase = 0;
+    auto issue_qk_tile = [&](int tile) {   // S(tile) = Q K(tile)^T over the 8 d-chunks
+      const uint32_t tS = tmem_base + (tile & 1) * BKV;
+      for (int c = 0; c < D5_CHUNKS; ++c) {
+        ptx::mbar_wait(full0 + 8 * stage, phase);
+        ptx::tc_fence_after();
+        const uint64_t kd = ptx::smem_desc_sw128(ptx::smem_u32(sR + stage * TILE_BYTES));
+        const uint64_t qd = q0 + (uint64_t)c * CHUNK_DESC;
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) ptx::mma_ss(tS, qd + 2 * k, kd + 2 * k, idesc_qk, (c | k) != 0);
+          ptx::mma_commit(empty0 + 8 * stage);
+          if (c == D5_CHUNKS - 1) ptx::mma_commit(s_full0 + 8 * (tile & 1));
+        }
+        __syncwarp();
+        if (++stage == D5_STAGES) { stage = 0; phase ^= 1; }
+      }
+    };
+    ptx::mbar_wait(q_full, 0);
+    issue_qk_tile(0);
+    for (int j = 0; j < n_tiles; ++j) {
+      if (j + 1 < n_tiles) issue_qk_tile(j + 1);            // overwrites S/P buffer (j+1)&1: P(j-1) V was issued before -> in order
+      ptx::mbar_wait(p_full0 + 8 * (j & 1), (j >> 1) & 1);  // P(j) is in tensor memory (and O has been rescaled if needed)
+      ptx::tc_fence_after();
+      const uint32_t tP = tmem_base + (j & 1) * BKV;
+      for (int c = 0; c < D5_VCHUNKS; ++c) {
+        ptx::mbar_wait(full0 + 8 * stage, phase);
+        ptx::tc_fence_after();
+        const uint64_t vd = ptx::smem_desc_sw128(ptx::smem_u32(sR + stage * TILE_BYTES));
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k) ptx::mma_ts(tO + 64 * c, tP + 8 * k, vd + 128 * k, idesc_pv, (j != 0) || (k != 0));
+          ptx::mma_commit(empty0 + 8 * stage);
+          if (c == D5_VCHUNKS - 1) ptx::mma_commit(o_ready);
+        }
+        __syncwarp();
+        if (++stage == D5_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax: two threads per query row (64 key columns each)
+    const int ew = warp & 3, half = (warp - 4) >> 2;
+    const int r = ew * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(ew * 32) << 16;
+    constexpr int COLS = BKV / 2, OCOLS = D5_VHALF / 2;
+    const int col0 = half * COLS;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int valid = min(COLS, p.nkv - j * BKV - col0);  // may be <= 0 for the upper half of a ragged last tile
+      const uint32_t tS = tmem_base + (j & 1) * BKV + lane_off;
+      ptx::mbar_wait(s_full0 + 8 * (j & 1), (j >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t v[COLS];
+      ptx::tmem_ld32(tS + col0, reinterpret_cast<uint32_t(&)[32]>(v[0]));
+      ptx::tmem_ld32(tS + col0 + 32, reinterpret_cast<uint32_t(&)[32]>(v[32]));
+      ptx::tmem_wait_ld();
+      float mx = -INFINITY;
+      if (valid >= COLS) {
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < COLS; i += 4) {
+          m0 = fmaxf(m0, __uint_as_float(v[i])); m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+          m2 = fmaxf(m2, __uint_as_float(v[i + 2])); m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      } else {
+#pragma unroll
+        for (int i = 0; i < COLS; ++i)
+          if (i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      // both halves of a row agree on the maximum; the barrier also orders "both halves have read S(j)" before "P(j) overwrites it"
+      float* slot = xm + (j & 1) * 256;
+      slot[half * 128 + r] = mx;
+      ptx::tc_fence_before();
+      ptx::named_barrier_sync(1, 256);
+      ptx::tc_fence_after();
+      mx = fmaxf(mx, slot[(half ^ 1) * 128 + r]);
+      // lazy rescaling: the reference maximum only moves when the true maximum outgrew it by more than 2^8 (P <= 256, exact range)
+      const float m_true = mx * p.scale_log2;
+      const float m_new = (m_true > m + 8.f) ? m_true : m;
+      const float alpha = ex2(m - m_new);  // 0 on the first tile
+      const bool moved = m_new > m;
+      m = m_new;
+      uint32_t pk[COLS / 2];
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      if (valid >= COLS) {
+#pragma unroll
+        for (int i = 0; i < COLS; i += 4) {
+          const float p0 = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new)), p1 = ex2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_new));
+          const float p2 = ex2(fmaf(__uint_as_float(v[i + 2]), p.scale_log2, -m_new)), p3 = ex2(fmaf(__uint_as_float(v[i + 3]), p.scale_log2, -m_new));
+          s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+          pk[i >> 1] = ptx::pack_bf16(p0, p1);
+          pk[(i >> 1) + 1] = ptx::pack_bf16(p2, p3);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < COLS; i += 2) {
+          float p0 = 0.f, p1 = 0.f;
+          if (i < valid) p0 = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
+          if (i + 1 < valid) p1 = ex2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_new));
+          s0 += p0 + p1;
+          pk[i >> 1] = ptx::pack_bf16(p0, p1);
+        }
+      }
+      l = l * alpha + ((s0 + s1) + (s2 + s3));
+      if (j > 0 && __any_sync(0xffffffffu, moved)) {   // rare: bring this thread's 128 accumulator columns to the new scale
+        ptx::mbar_wait(o_ready, (j - 1) & 1);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < OCOLS; c += 32) {
+          uint32_t o[32];
+          ptx::tmem_ld32(tO + lane_off + half * OCOLS + c, o);
+          ptx::tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          ptx::tmem_st32(tO + lane_off + half * OCOLS + c, o);
+        }
+      }
+      ptx::tmem_st32(tS + half * (COLS / 2), reinterpret_cast<const uint32_t(&)[32]>(pk[0]));  // P(j) in place of S(j)
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(p_full0 + 8 * (j & 1));
+    }
+    // ---- output: O / l (row sum over both halves: identical references throughout)
+    {
+      float* slot = xm + (n_tiles & 1) * 256;
+      slot[half * 128 + r] = l;
+      ptx::named_barrier_sync(1, 256);
+      l += slot[(half ^ 1) * 128 + r];
+    }
+    ptx::mbar_wait(o_ready, (n_tiles - 1) & 1);
+    ptx::tc_fence_after();
+    const int qi = qt * BQ + r;
+    const float inv = 1.f / l;
+    bf16* orow = p.out + (size_t)b * p.out_batch_stride + (size_t)qi * p.out_pitch + vh * D5_VHALF + half * OCOLS;
+#pragma unroll 1
+    for (int c = 0; c < OCOLS; c += 32) {
+      uint32_t o[32];
+      ptx::tmem_ld32(tO + lane_off + half * OCOLS + c, o);
+      ptx::tmem_wait_ld();
+      if (qi < p.nq) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u;
+          u.x = ptx::pack_bf16(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+          u.y = ptx::pack_bf16(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+          u.z = ptx::pack_bf16(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+          u.w = ptx::pack_bf16(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c + i) = u;
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  ptx::pdl_trigger();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+constexpr size_t smem_d512(int d) { return (size_t)(d / 64 + D5_STAGES) * TILE_BYTES + 2 * 256 * 4 + (1 + 2 * D5_STAGES + 5) * 8 + 16 + 1024; }
+static_assert(smem_d512(512) <= 232448, "d=512 attention: shared memory over the 227 KiB per-CTA limit");
+
 constexpr size_t SMEM_SINGLE = 7 * TILE_BYTES + 10 * 8 + 16 + 1024;
 constexpr size_t SMEM_SHORT = 5 * TILE_BYTES + 10 * 8 + 16 + 1024;
 constexpr size_t SMEM_PAIR = (2 + 2 * PAIR_KV_STAGES + 4) * TILE_BYTES + 4 * 256 * 4 + 14 * 8 + 16 + 1024;
@@ -759,5 +1018,35 @@ extern "C" int ladi_attention_bf16(const ladi_attn_desc* d, void* stream_) {
     else if (variant == 5) LADI_CUDA(ladi_launch(attention_pair_kernel<false, true, true>, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
     else LADI_CUDA(ladi_launch(attention_pair_kernel<false, false>, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
   }
+  return LADI_OK;
+}
+
+extern "C" int ladi_attention_d512_bf16(const ladi_attn_desc* d, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LADI_CHECK(d != nullptr && d->q && d->k && d->v && d->out, "null attention operand");
+  LADI_CHECK(d->batch > 0 && d->heads == 1 && d->nq > 0 && d->nkv > 0, "d512 attention: one head, non-empty extents");
+  LADI_CHECK(d->q_pitch % 8 == 0 && d->k_pitch % 8 == 0 && d->v_pitch % 8 == 0 && d->out_pitch % 8 == 0, "pitches must be multiples of 8");
+  const int D5 = d->head_dim == 0 ? 512 : d->head_dim;
+  LADI_CHECK(D5 == 512 || D5 == 256, "wide attention: head_dim must be 512 (or 256), got %d", D5);
+  LADI_CHECK(d->q_pitch >= D5 && d->k_pitch >= D5 && d->v_pitch >= D5 && d->out_pitch >= D5, "pitch < head_dim");
+  LADI_CHECK((reinterpret_cast<uintptr_t>(d->out) & 15) == 0, "out must be 16-byte aligned");
+  CUtensorMap tq, tk, tv;
+  if (make_map(&tq, d->q, D5, d->nq, d->batch, d->q_pitch, d->q_batch_stride)) return LADI_ERR_CUDA;
+  if (make_map(&tk, d->k, D5, d->nkv, d->batch, d->k_pitch, d->k_batch_stride)) return LADI_ERR_CUDA;
+  if (make_map(&tv, d->v, D5, d->nkv, d->batch, d->v_pitch, d->v_batch_stride)) return LADI_ERR_CUDA;
+  AttnParams p;
+  p.nq = d->nq; p.nkv = d->nkv; p.n_kv_tiles = (d->nkv + BKV - 1) / BKV;
+  p.out = reinterpret_cast<bf16*>(d->out); p.out_pitch = d->out_pitch; p.out_batch_stride = d->out_batch_stride;
+  p.scale_log2 = d->scale * 1.4426950408889634f;
+  p.b_delay = 0; p.trace = nullptr;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LADI_CUDA(cudaFuncSetAttribute(attention_d512_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d512(512)));
+    LADI_CUDA(cudaFuncSetAttribute(attention_d512_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d512(256)));
+    attr_set = true;
+  }
+  dim3 grid((d->nq + BQ - 1) / BQ, D5 / D5_VHALF, d->batch);
+  if (D5 == 512) LADI_CUDA(ladi_launch(attention_d512_kernel<512>, grid, dim3(384), smem_d512(512), stream, tq, tk, tv, p));
+  else LADI_CUDA(ladi_launch(attention_d512_kernel<256>, grid, dim3(384), smem_d512(256), stream, tq, tk, tv, p));
   return LADI_OK;
 }

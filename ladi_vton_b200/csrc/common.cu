@@ -15,7 +15,7 @@ void ladi_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* ladi_last_error(void) { return g_err; }
-extern "C" int ladi_abi_version(void) { return 1; }
+extern "C" int ladi_abi_version(void) { return 2; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

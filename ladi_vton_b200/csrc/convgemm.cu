@@ -57,13 +57,23 @@ struct KParams {
   void* out;
   int out_pitch;
   int out_fp32;
+  // LayerNorm folded into the GEMMs on either side of it (BasicTransformerBlock.norm1/2/3):
+  float2* rowstat_out;        // producer: per (row, 32-column chunk) {sum, sum of squares} of the values this GEMM stores
+  int rowstat_chunks;         //           = c_out / 32
+  const float2* ln_stats;     // consumer: the producer's table for this GEMM's A rows; out = rstd*(acc - mean*colsum[c]) + bias[c]
+  int ln_chunks;              //           = K / 32 (the normalised width)
+  const float* ln_colsum;     //           [c_out] fp32: sum_k of the (gamma-scaled, bf16-rounded) weight row
+  float ln_eps;
+  // nearest-2x upsample fused into a 3x3 convolution (diffusers Upsample2D): the 4 output parities are 4 groups of M tiles, each a
+  // 2x2-tap convolution over the half-resolution input with its own merged weights and a strided output tensor map
+  int up2x, tiles_pp;         // tiles_pp = M tiles per parity plane
 };
 
 struct AMaps {
   CUtensorMap m[NUM_A_MAPS];
 };
 struct EMaps {            // epilogue tensor maps: 64-column (SWIZZLE_128B) and 32-column (SWIZZLE_64B) boxes
-  CUtensorMap out64, out32, res64, res32;
+  CUtensorMap out64[4], out32[4], res64, res32;   // out maps indexed by output parity (index 0 unless up2x)
 };
 
 // x * sigmoid(x) = h * (1 + tanh(h)), h = x / 2: one MUFU op (tanh.approx, relative error 2^-11, below bf16 output resolution)
@@ -95,12 +105,17 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 
 struct TileCoord {
-  int nt, x0, y0, n0;
+  int nt, x0, y0, n0, par;
 };
 __device__ __forceinline__ TileCoord tile_coord(const KParams& p, int tile) {
   TileCoord t;
-  const int mt = tile / p.tiles_n;
+  int mt = tile / p.tiles_n;
   t.nt = tile - mt * p.tiles_n;
+  t.par = 0;
+  if (p.up2x) {
+    t.par = mt / p.tiles_pp;
+    mt -= t.par * p.tiles_pp;
+  }
   const int tb = mt / (p.tiles_y * p.tiles_x);
   const int rem = mt - tb * (p.tiles_y * p.tiles_x);
   const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
@@ -141,7 +156,7 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
     for (int s = 0; s < p.nseg; ++s) ptx::prefetch_tmap(&amaps.m[p.seg[s].map]);
     ptx::prefetch_tmap(&tmB);
     if (p.staged) {
-      ptx::prefetch_tmap(&emaps.out64);
+      ptx::prefetch_tmap(&emaps.out64[0]);
       if (p.residual != nullptr) ptx::prefetch_tmap(&emaps.res64);
     }
     for (int s = 0; s < STAGES; ++s) {
@@ -206,12 +221,14 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
               // both CTAs' bytes are credited to the leader's barrier, which alone expects them
               if (rank == 0) ptx::mbar_expect_tx(fb, 2 * (A_BYTES + B_BYTES));
               const uint32_t fl = full_leader0 + 8 * stage;
-              ptx::tma_load_4d_pair(am, ptx::smem_u32(sA + stage * A_BYTES), fl, sg.c_begin + c * BK, tc.x0 + sg.dx, tc.y0 + sg.dy, tc.n0);
-              ptx::tma_load_2d_pair(&tmB, ptx::smem_u32(sB + stage * B_BYTES), fl, kb * BK, tc.nt * BN + (int)rank * B_ROWS);
+              ptx::tma_load_4d_pair(am, ptx::smem_u32(sA + stage * A_BYTES), fl, sg.c_begin + c * BK, tc.x0 + sg.dx + (tc.par & 1),
+                                    tc.y0 + sg.dy + (tc.par >> 1), tc.n0);
+              ptx::tma_load_2d_pair(&tmB, ptx::smem_u32(sB + stage * B_BYTES), fl, kb * BK, tc.par * p.c_out + tc.nt * BN + (int)rank * B_ROWS);
             } else {
               ptx::mbar_expect_tx(fb, A_BYTES + B_BYTES);
-              ptx::tma_load_4d(am, ptx::smem_u32(sA + stage * A_BYTES), fb, sg.c_begin + c * BK, tc.x0 + sg.dx, tc.y0 + sg.dy, tc.n0);
-              ptx::tma_load_2d(&tmB, ptx::smem_u32(sB + stage * B_BYTES), fb, kb * BK, tc.nt * BN);
+              ptx::tma_load_4d(am, ptx::smem_u32(sA + stage * A_BYTES), fb, sg.c_begin + c * BK, tc.x0 + sg.dx + (tc.par & 1),
+                               tc.y0 + sg.dy + (tc.par >> 1), tc.n0);
+              ptx::tma_load_2d(&tmB, ptx::smem_u32(sB + stage * B_BYTES), fb, kb * BK, tc.par * p.c_out + tc.nt * BN);
             }
           }
           __syncwarp();
@@ -310,6 +327,24 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
         const size_t grow = ((size_t)n * p.H + y) * p.W + x;
         const float rscale = (p.row_scale != nullptr && row_ok) ? p.row_scale[grow] : 1.f;
         const float rbias = (p.bias_per_row && bias != nullptr && row_ok) ? bias[grow] : 0.f;
+        // folded LayerNorm (consumer side): mean / rstd of this A row from the producer's per-chunk partial sums, summed in chunk
+        // order (deterministic); issued before the accumulator wait so the loads overlap the main loop's tail
+        float ln_a = 1.f, ln_b = 0.f;
+        if (p.ln_stats != nullptr) {
+          float s_ = 0.f, q_ = 0.f;
+          if (row_ok) {
+            const float4* st = reinterpret_cast<const float4*>(p.ln_stats + grow * p.ln_chunks);  // ln_chunks is even
+            for (int c = 0; c < (p.ln_chunks >> 1); ++c) {
+              const float4 u = __ldg(st + c);
+              s_ += u.x; q_ += u.y; s_ += u.z; q_ += u.w;
+            }
+          }
+          const float inv_c = 1.f / (32.f * (float)p.ln_chunks);
+          const float mean = s_ * inv_c;
+          const float var = fmaxf(q_ * inv_c - mean * mean, 0.f);
+          ln_a = rsqrtf(var + p.ln_eps);
+          ln_b = -ln_a * mean;
+        }
 
         ptx::mbar_wait(tfull0 + 8 * as, aphase);
         ptx::tc_fence_after();
@@ -343,6 +378,14 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
             const int gcol = acc0 + acol;                            // global accumulator column (bias index)
+            if (p.ln_stats != nullptr && gcol + 32 <= p.c_out) {      // rstd * (x W'^T) - rstd * mean * colsum(W')   (c_out % 32 == 0)
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + gcol + j));
+                f[j] = fmaf(ln_b, c4.x, ln_a * f[j]); f[j + 1] = fmaf(ln_b, c4.y, ln_a * f[j + 1]);
+                f[j + 2] = fmaf(ln_b, c4.z, ln_a * f[j + 2]); f[j + 3] = fmaf(ln_b, c4.w, ln_a * f[j + 3]);
+              }
+            }
             if (bias != nullptr) {
               if (p.bias_per_row) {
 #pragma unroll
@@ -380,6 +423,7 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
             }
+            float rs0 = 0.f, rs1 = 0.f, rq0 = 0.f, rq1 = 0.f;        // row statistics of this 32-column chunk (rowstat_out)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {                            // 4 pieces of 8 columns (16 bytes of bf16)
               const int piece = 4 * c + q;                           // piece index within the slab row
@@ -390,10 +434,18 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
                 g[0] += ptx::bf16_lo(u.x); g[1] += ptx::bf16_hi(u.x); g[2] += ptx::bf16_lo(u.y); g[3] += ptx::bf16_hi(u.y);
                 g[4] += ptx::bf16_lo(u.z); g[5] += ptx::bf16_hi(u.z); g[6] += ptx::bf16_lo(u.w); g[7] += ptx::bf16_hi(u.w);
               }
+              if (p.rowstat_out != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 8; k += 2) {
+                  rs0 += g[k]; rq0 = fmaf(g[k], g[k], rq0);
+                  rs1 += g[k + 1]; rq1 = fmaf(g[k + 1], g[k + 1], rq1);
+                }
+              }
               *reinterpret_cast<uint4*>(ostage + off) =
                   make_uint4(ptx::pack_bf16(g[0] * rscale, g[1] * rscale), ptx::pack_bf16(g[2] * rscale, g[3] * rscale),
                              ptx::pack_bf16(g[4] * rscale, g[5] * rscale), ptx::pack_bf16(g[6] * rscale, g[7] * rscale));
             }
+            if (p.rowstat_out != nullptr && row_ok && gcol + 32 <= p.c_out) p.rowstat_out[grow * p.rowstat_chunks + (gcol >> 5)] = make_float2(rs0 + rs1, rq0 + rq1);
           }
           if (has_res) ++rcount;
           ptx::fence_proxy_async_smem();                 // staging writes -> visible to the TMA engine
@@ -401,7 +453,7 @@ convgemm_kernel(const __grid_constant__ AMaps amaps, const __grid_constant__ CUt
           ptx::named_barrier_sync(1, 256);
           if (elected) {
             if (ocol < c_eff) {
-              ptx::tma_store_4d(wout == 64 ? &emaps.out64 : &emaps.out32, ptx::smem_u32(ostage), ocol, tc.x0, tc.y0, tc.n0);
+              ptx::tma_store_4d(wout == 64 ? &emaps.out64[tc.par] : &emaps.out32[tc.par], ptx::smem_u32(ostage), ocol, tc.x0, tc.y0, tc.n0);
               ptx::tma_store_commit();
             }
             if (has_res) issue_residual();  // the ring slot every thread just finished reading is free again
@@ -613,25 +665,41 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
   LADI_CHECK(d->act >= 0 && d->act <= 4, "bad act");
   LADI_CHECK(d->act != 2 || (d->c_out % 2 == 0 && !d->out_fp32 && d->residual == nullptr), "GEGLU needs even c_out, bf16 out");
   LADI_CHECK(d->out != nullptr && d->weight != nullptr, "null out/weight");
+  const int up = d->up2x ? 1 : 0;
+  if (up) {
+    LADI_CHECK(d->ksize == 3 && d->stride == 1 && d->n_sc == 0, "up2x: 3x3 stride-1 convolution without fused shortcut only");
+    LADI_CHECK(d->h_out % 2 == 0 && d->w_out % 2 == 0, "up2x: output extent must be even");
+    LADI_CHECK(d->residual == nullptr && d->row_scale == nullptr && !d->bias_per_row && d->act != 2 && !d->out_fp32,
+               "up2x: bf16 output with per-channel bias / SiLU / GELU / ReLU only");
+  }
+  LADI_CHECK(d->rowstat_out == nullptr || (d->c_out % 32 == 0 && d->act != 2 && d->row_scale == nullptr && !d->out_fp32 && !up),
+             "rowstat_out: c_out %% 32 == 0, bf16 out, no GEGLU / row_scale");
+  LADI_CHECK(d->ln_stats == nullptr || (d->ln_colsum != nullptr && d->c_out % 32 == 0 && d->ksize == 1 && d->n_src == 1 && d->n_sc == 0 &&
+                                        d->src_c[0] % 64 == 0 && !d->out_fp32 && !d->bias_per_row && !up),
+             "ln_stats: GEMM over one source of K %% 64 == 0, c_out %% 32 == 0, bf16 out, ln_colsum given");
 
   KParams kp;
   memset(&kp, 0, sizeof(kp));
   AMaps am;
   EMaps em;
-  kp.n_img = d->n; kp.H = d->h_out; kp.W = d->w_out; kp.c_out = d->c_out;
-  kp.bw = largest_pow2_divisor(d->w_out, 128);
+  // up2x: the tile grid covers ONE output parity plane (h_out/2 x w_out/2 pixels = the input extent); tiles_m counts all four
+  const int HO = up ? d->h_out / 2 : d->h_out, WO = up ? d->w_out / 2 : d->w_out;
+  kp.n_img = d->n; kp.H = HO; kp.W = WO; kp.c_out = d->c_out;
+  kp.bw = largest_pow2_divisor(WO, 128);
   if (d->ksize == 1 && d->h_out == 1 && d->stride == 1) kp.bw = 128;  // plain GEMM: row tail handled by OOB fill
-  kp.bh = largest_pow2_divisor(d->h_out, 128 / kp.bw);
+  kp.bh = largest_pow2_divisor(HO, 128 / kp.bw);
   kp.bn = 128 / (kp.bw * kp.bh);
-  kp.tiles_x = (d->w_out + kp.bw - 1) / kp.bw;
-  kp.tiles_y = (d->h_out + kp.bh - 1) / kp.bh;
+  kp.tiles_x = (WO + kp.bw - 1) / kp.bw;
+  kp.tiles_y = (HO + kp.bh - 1) / kp.bh;
   kp.tiles_b = (d->n + kp.bn - 1) / kp.bn;
   kp.tiles_m = kp.tiles_x * kp.tiles_y * kp.tiles_b;
+  kp.up2x = up; kp.tiles_pp = kp.tiles_m;
+  if (up) kp.tiles_m *= 4;
 
   // ---- A tensor maps: one per (source, parity plane)
   int nmaps = 0;
   const int s = d->stride;
-  const int h_in = d->h_in > 0 ? d->h_in : d->h_out * s, w_in = d->w_in > 0 ? d->w_in : d->w_out * s;
+  const int h_in = up ? HO : (d->h_in > 0 ? d->h_in : d->h_out * s), w_in = up ? WO : (d->w_in > 0 ? d->w_in : d->w_out * s);
   const uint32_t box[4] = {(uint32_t)BK, (uint32_t)kp.bw, (uint32_t)kp.bh, (uint32_t)kp.bn};
   int src_map0[2] = {0, 0}, sc_map0[2] = {0, 0};
   for (int i = 0; i < d->n_src; ++i) {
@@ -662,11 +730,12 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
 
   // ---- K segments: taps (row-major) x sources, then the shortcut sources.  Weight K order must match (see packer).
   int nseg = 0, total = 0;
-  const int taps = d->ksize * d->ksize;
+  const int taps = up ? 4 : d->ksize * d->ksize;
   for (int t = 0; t < taps; ++t) {
-    const int ky = d->ksize == 3 ? t / 3 : 0, kx = d->ksize == 3 ? t % 3 : 0;
+    const int ky = up ? t / 2 : (d->ksize == 3 ? t / 3 : 0), kx = up ? t % 2 : (d->ksize == 3 ? t % 3 : 0);
     // input coordinate = out*stride + k - pad_lo;  parity plane p = (k - pad_lo) mod s, shift = floor((k - pad_lo) / s)
-    const int oy = ky - (d->ksize == 3 ? d->pad_lo : 0), ox = kx - (d->ksize == 3 ? d->pad_lo : 0);
+    // up2x: output pixel 2i+p reads input pixels i+p-1 and i+p (merged taps); the kernel adds the parity p, so the base shift is t-1
+    const int oy = up ? ky - 1 : ky - (d->ksize == 3 ? d->pad_lo : 0), ox = up ? kx - 1 : kx - (d->ksize == 3 ? d->pad_lo : 0);
     const int py = ((oy % s) + s) % s, px = ((ox % s) + s) % s;
     const int dy = (oy - py) / s, dx = (ox - px) / s;
     for (int i = 0; i < d->n_src; ++i) {
@@ -694,6 +763,8 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
   kp.bias = d->bias; kp.bias_per_row = d->bias_per_row; kp.bias_step_stride = d->bias_step_stride; kp.step_ptr = d->step_ptr;
   kp.residual = reinterpret_cast<const bf16*>(d->residual); kp.residual_pitch = d->residual_pitch;
   kp.row_scale = d->row_scale; kp.act = d->act; kp.out = d->out; kp.out_pitch = d->out_pitch; kp.out_fp32 = d->out_fp32;
+  kp.rowstat_out = reinterpret_cast<float2*>(d->rowstat_out); kp.rowstat_chunks = d->c_out / 32;
+  kp.ln_stats = reinterpret_cast<const float2*>(d->ln_stats); kp.ln_chunks = d->src_c[0] / 32; kp.ln_colsum = d->ln_colsum; kp.ln_eps = d->ln_eps;
 
   // ---- epilogue flavour: staged TMA stores need bf16 output with 16-byte aligned rows
   const int c_eff = d->act == 2 ? d->c_out / 2 : d->c_out;
@@ -726,13 +797,16 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
     }
   }
   if (d->act == 2 && kp.staged && BN % 128 != 0) kp.staged = 0;
+  LADI_CHECK(kp.staged || (!up && d->rowstat_out == nullptr && d->ln_stats == nullptr),
+             "up2x / rowstat_out / ln_stats need the staged epilogue (bf16 out, 16-byte aligned rows)");
 
   // ---- split-K: few output tiles but a long reduction (the 8x6 / 16x12 UNet levels): spread K over otherwise idle SMs,
   // fp32 partial planes in the caller's workspace, summed (in split order) by splitk_reduce_kernel
   kp.splits = 1; kp.kb_per_split = total; kp.split_stride = 0;
   const long long rows = (long long)d->n * d->h_out * d->w_out;
   bool split = false;
-  if (d->splitk_ws != nullptr && d->force_bn == 0 && !d->out_fp32 && d->act != 2 && d->row_scale == nullptr && !d->bias_per_row &&
+  if (d->splitk_ws != nullptr && d->force_bn == 0 && !d->out_fp32 && d->act != 2 && d->row_scale == nullptr && !d->bias_per_row && !up &&
+      d->rowstat_out == nullptr && d->ln_stats == nullptr &&
       d->c_out % 4 == 0 && d->out_pitch % 4 == 0 && (d->residual == nullptr || d->residual_pitch % 4 == 0) && total >= 32) {
     const int bn_s = d->c_out >= 256 ? 256 : (d->c_out >= 128 ? 128 : 64);
     const long tiles_s = (long)kp.tiles_m * ((d->c_out + bn_s - 1) / bn_s);
@@ -757,7 +831,7 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
   // ---- CTA pairs (tcgen05 cta_group::2): two M tiles per cluster share one N tile; needs >= 2 M tiles, no split-K, and a B half
   // of whole 8-row swizzle groups.  pair_mode: 0 = library default (on; env LADI_CONV_2CTA=0 turns it off), 1 = force, 2 = never.
   bool pair = false;
-  if (!split && kp.tiles_m >= 2 && BN >= 128 && BN % 16 == 0) {
+  if (!split && kp.tiles_m >= 2 && BN >= 128 && BN % 16 == 0 && (!up || kp.tiles_pp % 2 == 0)) {  // up2x: a pair shares one parity's weights
     if (d->pair_mode == 1) pair = true;
     // default: pair whenever there are enough M tiles that the phantom tile of an odd count is noise (measured 1.03-1.26x on every
     // UNet shape, profiles/r01_pair_bench.jsonl)
@@ -767,7 +841,7 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
 
   CUtensorMap tmB;
   {
-    const uint64_t dims[2] = {(uint64_t)d->k_total, (uint64_t)d->c_out};
+    const uint64_t dims[2] = {(uint64_t)d->k_total, (uint64_t)d->c_out * (up ? 4 : 1)};  // up2x: the four parities' merged weights, stacked
     const uint64_t strides[1] = {(uint64_t)d->weight_pitch * 2};
     const uint32_t bbox[2] = {(uint32_t)BK, (uint32_t)(pair ? BN / 2 : BN)};
     if (ladi_encode_tmap_bf16(&tmB, d->weight, 2, dims, strides, bbox)) return LADI_ERR_CUDA;
@@ -775,16 +849,29 @@ extern "C" int ladi_conv2d_bf16(const ladi_conv_desc* d, void* stream_) {
   if (kp.staged) {
     const uint32_t box64[4] = {64u, (uint32_t)kp.bw, (uint32_t)kp.bh, (uint32_t)kp.bn};
     const uint32_t box32[4] = {32u, (uint32_t)kp.bw, (uint32_t)kp.bh, (uint32_t)kp.bn};
-    if (encode_nhwc_map(&em.out64, d->out, c_eff, d->out_pitch, d->w_out, d->h_out, d->n, box64, 128)) return LADI_ERR_CUDA;
-    if (encode_nhwc_map(&em.out32, d->out, c_eff, d->out_pitch, d->w_out, d->h_out, d->n, box32, 64)) return LADI_ERR_CUDA;
+    if (up) {  // one strided map per output parity: pixel (2i+py, 2j+px) of the full-resolution tensor
+      for (int par = 0; par < 4; ++par) {
+        const uint64_t pitch = (uint64_t)d->out_pitch;
+        const uint64_t dims[4] = {(uint64_t)c_eff, (uint64_t)WO, (uint64_t)HO, (uint64_t)d->n};
+        const uint64_t strides[3] = {pitch * 2 * 2, pitch * 2 * d->w_out * 2, pitch * 2 * (uint64_t)d->w_out * d->h_out};
+        const bf16* base = reinterpret_cast<const bf16*>(d->out) + ((size_t)(par >> 1) * d->w_out + (par & 1)) * pitch;
+        if (ladi_encode_tmap_bf16(&em.out64[par], base, 4, dims, strides, box64, 128)) return LADI_ERR_CUDA;
+        if (ladi_encode_tmap_bf16(&em.out32[par], base, 4, dims, strides, box32, 64)) return LADI_ERR_CUDA;
+      }
+    } else {
+      if (encode_nhwc_map(&em.out64[0], d->out, c_eff, d->out_pitch, d->w_out, d->h_out, d->n, box64, 128)) return LADI_ERR_CUDA;
+      if (encode_nhwc_map(&em.out32[0], d->out, c_eff, d->out_pitch, d->w_out, d->h_out, d->n, box32, 64)) return LADI_ERR_CUDA;
+      for (int par = 1; par < 4; ++par) { em.out64[par] = em.out64[0]; em.out32[par] = em.out32[0]; }
+    }
     if (d->residual != nullptr) {
       if (encode_nhwc_map(&em.res64, d->residual, c_eff, d->residual_pitch, d->w_out, d->h_out, d->n, box64, 128)) return LADI_ERR_CUDA;
       if (encode_nhwc_map(&em.res32, d->residual, c_eff, d->residual_pitch, d->w_out, d->h_out, d->n, box32, 64)) return LADI_ERR_CUDA;
     } else {
-      em.res64 = em.out64; em.res32 = em.out32;
+      em.res64 = em.out64[0]; em.res32 = em.out32[0];
     }
   } else {
-    em.out64 = em.out32 = em.res64 = em.res32 = tmB;
+    for (int par = 0; par < 4; ++par) em.out64[par] = em.out32[par] = tmB;
+    em.res64 = em.res32 = tmB;
   }
   int rc = LADI_OK;
   switch (BN) {

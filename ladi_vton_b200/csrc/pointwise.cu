@@ -492,10 +492,10 @@ __global__ void bilinear8_kernel(const float* __restrict__ x, int nc, int H, int
 
 __global__ void ddim_cfg_kernel(const float* __restrict__ eps, int eps_pitch, float* __restrict__ lat, bf16* __restrict__ uin,
                                 int in_pitch, int B, int hw, int cfg, float guidance, const float* __restrict__ coef, int* step_ptr,
-                                int advance) {
+                                int advance, const float* __restrict__ noise) {
   ptx::pdl_wait();
   const int s = step_ptr ? step_ptr[0] : 0;
-  const float inv_sa = coef[4 * s], s1a = coef[4 * s + 1], sap = coef[4 * s + 2], s1ap = coef[4 * s + 3];
+  const float inv_sa = coef[8 * s], s1a = coef[8 * s + 1], sap = coef[8 * s + 2], s1ap = coef[8 * s + 3], sigma = coef[8 * s + 4];
   const int64_t total = (int64_t)B * 4 * hw;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t px = i % hw;
@@ -509,7 +509,8 @@ __global__ void ddim_cfg_kernel(const float* __restrict__ eps, int eps_pitch, fl
     }
     const float x = lat[i];
     const float x0 = (x - s1a * e) * inv_sa;
-    const float xn = sap * x0 + s1ap * e;
+    float xn = sap * x0 + s1ap * e;
+    if (noise != nullptr) xn += sigma * noise[i];  // eta > 0: DDIMScheduler.step's variance noise
     lat[i] = xn;
     const bf16 hb = __float2bfloat16(xn);
     uin[(b * hw + px) * in_pitch + ch] = hb;
@@ -526,6 +527,27 @@ __global__ void ddim_cfg_kernel(const float* __restrict__ eps, int eps_pitch, fl
       }
     }
   }
+}
+
+// prepare_mask_and_masked_image's range checks and in-place mask binarisation (tryon_pipe.py:630) without a host round trip: the two
+// flags are OR-ed into device memory and read by the pipeline together with the result.  NaN compares false, like the reference's
+// `x.min() < lo or x.max() > hi`.
+__global__ void check_binarise_kernel(const float* __restrict__ image, int64_t n_image, float* __restrict__ mask, int64_t n_mask,
+                                      int* __restrict__ flags) {
+  ptx::pdl_wait();
+  bool bad_i = false, bad_m = false;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_image; i += stride) {
+    const float v = image[i];
+    bad_i |= (v < -1.f) | (v > 1.f);
+  }
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_mask; i += stride) {
+    const float v = mask[i];
+    bad_m |= (v < 0.f) | (v > 1.f);
+    mask[i] = v < 0.5f ? 0.f : (v >= 0.5f ? 1.f : v);  // mask[mask < 0.5] = 0; mask[mask >= 0.5] = 1 (NaN stays)
+  }
+  if (__any_sync(0xffffffffu, bad_i) && (threadIdx.x & 31) == 0) atomicOr(flags, 1);
+  if (__any_sync(0xffffffffu, bad_m) && (threadIdx.x & 31) == 0) atomicOr(flags + 1, 1);
 }
 
 __global__ void image_out_kernel(const void* __restrict__ x, int is_f32, int64_t npx, int x_pitch, float* __restrict__ out) {
@@ -710,10 +732,17 @@ extern "C" int ladi_bilinear_down8(const float* x, int n, int c, int H, int W, f
 }
 
 extern "C" int ladi_ddim_cfg_step(const float* eps, int eps_pitch, float* latents, void* unet_in, int in_pitch, int B, int h, int w,
-                                  int cfg, float guidance, const float* coef, int* step_ptr, int advance, void* stream) {
+                                  int cfg, float guidance, const float* coef, int* step_ptr, int advance, const float* noise, void* stream) {
   LADI_CHECK(eps && latents && unet_in && coef, "ddim: null operand");
   LADI_CUDA(ladi_launch(ddim_cfg_kernel, dim3(grid_for((int64_t)B * 4 * h * w)), dim3(256), 0, STREAM, eps, eps_pitch, latents, (bf16*)unet_in, in_pitch, B, h * w, cfg,
-                                                                         guidance, coef, step_ptr, advance));
+                                                                         guidance, coef, step_ptr, advance, noise));
+  return LADI_OK;
+}
+
+extern "C" int ladi_check_binarise(const float* image, long long n_image, float* mask, long long n_mask, int* flags, void* stream) {
+  LADI_CHECK(image && mask && flags && n_image > 0 && n_mask > 0, "check_binarise: bad arguments");
+  const long long total = n_image > n_mask ? n_image : n_mask;
+  LADI_CUDA(ladi_launch(check_binarise_kernel, dim3(grid_for((total + 3) / 4)), dim3(256), 0, STREAM, image, (int64_t)n_image, mask, (int64_t)n_mask, flags));
   return LADI_OK;
 }
 

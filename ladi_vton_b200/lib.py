@@ -23,6 +23,8 @@ class ConvDesc(C.Structure):
         ("row_scale", C.c_void_p), ("act", C.c_int),
         ("out", C.c_void_p), ("out_pitch", C.c_int), ("out_fp32", C.c_int), ("force_bn", C.c_int), ("force_direct_epilogue", C.c_int), ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_int64),
         ("pair_mode", C.c_int),
+        ("rowstat_out", C.c_void_p), ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("ln_eps", C.c_float),
+        ("up2x", C.c_int),
     ]
 
 
@@ -33,7 +35,7 @@ class AttnDesc(C.Structure):
         ("k", C.c_void_p), ("k_pitch", C.c_int), ("k_batch_stride", C.c_int64),
         ("v", C.c_void_p), ("v_pitch", C.c_int), ("v_batch_stride", C.c_int64),
         ("out", C.c_void_p), ("out_pitch", C.c_int), ("out_batch_stride", C.c_int64),
-        ("scale", C.c_float), ("variant", C.c_int), ("trace", C.c_void_p),
+        ("scale", C.c_float), ("variant", C.c_int), ("trace", C.c_void_p), ("head_dim", C.c_int),
     ]
 
 
@@ -43,6 +45,7 @@ SIGNATURES = {
     "ladi_last_error": ([], C.c_char_p),
     "ladi_conv2d_bf16": ([C.POINTER(ConvDesc), _P], _I),
     "ladi_attention_bf16": ([C.POINTER(AttnDesc), _P], _I),
+    "ladi_attention_d512_bf16": ([C.POINTER(AttnDesc), _P], _I),
     "ladi_groupnorm_chunks": ([_I], _I),
     "ladi_groupnorm_stats": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P], _I),
     "ladi_groupnorm_apply": ([_P, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _F, _I, _P, _I, _P, _I, _P], _I),
@@ -56,7 +59,8 @@ SIGNATURES = {
     "ladi_posterior_sample": ([_P, _I, _P, _I, _I, _I, _I, _F, _P, _P], _I),
     "ladi_inv_mask_rows": ([_P, _I, _I, _I, _I, _P, _P], _I),
     "ladi_bilinear_down8": ([_P, _I, _I, _I, _I, _P, _P], _I),
-    "ladi_ddim_cfg_step": ([_P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _I, _P], _I),
+    "ladi_ddim_cfg_step": ([_P, _I, _P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _I, _P, _P], _I),
+    "ladi_check_binarise": ([_P, _L, _P, _L, _P, _P], _I),
     "ladi_image_out": ([_P, _I, _I, _I, _I, _I, _P, _P], _I),
     "ladi_image_out_u8": ([_P, _I, _I, _I, _I, _I, _P, _P], _I),
     "ladi_pose_heatmaps": ([_P, _I, _I, _I, _F, _P, _P], _I),
@@ -77,6 +81,7 @@ SIGNATURES = {
     "ladi_nhwc_f32_to_nchw_clamp": ([_P, _I, _I, _I, _I, _I, _F, _F, _P, _P], _I),
 }
 
+ABI_VERSION = 2
 _lib = None
 launches = 0  # number of kernel-launching ABI calls made by this process (bench.py reports it as gpu_launches)
 
@@ -93,7 +98,7 @@ def load():
     for name, (argtypes, restype) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.argtypes, fn.restype = argtypes, restype
-    if lib.ladi_abi_version() != 1:
+    if lib.ladi_abi_version() != ABI_VERSION:
         raise RuntimeError("libladi_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -63,18 +63,25 @@ def padded_k(channels):
 
 def conv2d(srcs, weight, c_out, *, ksize=3, stride=1, pad_lo=1, shortcut=(), bias=None, bias_per_row=False,
            bias_step_stride=0, step_ptr=None, residual=None, row_scale=None, act=ACT_NONE, out=None, out_fp32=False,
-           force_bn=0, direct_epilogue=False, split_k=True, pair=None):
+           force_bn=0, direct_epilogue=False, split_k=True, pair=None, rowstat=None, ln=None, up2x=False):
     """Implicit-GEMM convolution over the channel-concat of `srcs` (+ fused 1x1 over `shortcut` tensors).
-    `weight`: packed bf16 [c_out, k_total] (see weights.pack_conv).  Returns the NHWC output tensor."""
+    `weight`: packed bf16 [c_out, k_total] (see weights.pack_conv).  Returns the NHWC output tensor.
+    rowstat: fp32 [rows, c_out/32, 2] table this call fills with per-row partial {sum, sum of squares} (LayerNorm producer side);
+    ln = (stats table of the A rows, colsum fp32 [c_out], eps): LayerNorm folded into this GEMM (weights.fold_layernorm);
+    up2x: `srcs` are half-resolution, `weight` = weights.pack_conv_up2x (nearest-2x upsample fused into the 3x3 conv)."""
     assert 1 <= len(srcs) <= 2 and len(shortcut) <= 2
     d = ConvDesc()
     n, h_in, w_in, _, _ = _nhwc(srcs[0])
-    if ksize == 3 and stride == 2:
+    if up2x:
+        assert ksize == 3 and stride == 1
+        h_out, w_out = 2 * h_in, 2 * w_in
+    elif ksize == 3 and stride == 2:
         h_out, w_out = (h_in + (2 if pad_lo == 1 else 1) - 3) // 2 + 1, (w_in + (2 if pad_lo == 1 else 1) - 3) // 2 + 1
     else:
         h_out, w_out = h_in, w_in
     d.n, d.h_out, d.w_out, d.c_out = n, h_out, w_out, c_out
     d.h_in, d.w_in = h_in, w_in
+    d.up2x = int(bool(up2x))
     d.ksize, d.stride, d.pad_lo = ksize, stride, pad_lo
     d.n_src = len(srcs)
     for i, s in enumerate(srcs):
@@ -88,7 +95,7 @@ def conv2d(srcs, weight, c_out, *, ksize=3, stride=1, pad_lo=1, shortcut=(), bia
         sn, sh, sw, sc, sp = _nhwc(s)
         assert (sn, sh, sw) == (n, h_out, w_out)
         d.sc[i], d.sc_c[i], d.sc_pitch[i] = s.data_ptr(), sc, sp
-    assert weight.dtype == torch.bfloat16 and weight.dim() == 2 and weight.stride(1) == 1 and weight.shape[0] >= c_out
+    assert weight.dtype == torch.bfloat16 and weight.dim() == 2 and weight.stride(1) == 1 and weight.shape[0] >= (4 * c_out if up2x else c_out)
     d.weight, d.k_total, d.weight_pitch = weight.data_ptr(), weight.shape[1], weight.stride(0)
     if bias is not None:
         assert bias.dtype == torch.float32
@@ -96,7 +103,8 @@ def conv2d(srcs, weight, c_out, *, ksize=3, stride=1, pad_lo=1, shortcut=(), bia
     d.step_ptr = step_ptr.data_ptr() if step_ptr is not None else 0
     c_eff = c_out // 2 if act == ACT_GEGLU else c_out
     if out is None:
-        out = torch.empty((n, h_out, w_out, c_eff), dtype=torch.float32 if out_fp32 else torch.bfloat16, device=srcs[0].device)
+        c_alloc = c_eff if (out_fp32 or c_eff % 8 == 0) else (c_eff + 7) // 8 * 8  # bf16 rows stay 16-byte aligned (a later conv reads them by TMA)
+        out = torch.empty((n, h_out, w_out, c_alloc), dtype=torch.float32 if out_fp32 else torch.bfloat16, device=srcs[0].device)[..., :c_eff]
     on, oh, ow, oc, op = (out.shape[0], out.shape[1], out.shape[2], out.shape[3], out.stride(2))
     assert (on, oh, ow) == (n, h_out, w_out) and oc >= c_eff and out.stride(3) == 1
     assert out.dtype == (torch.float32 if out_fp32 else torch.bfloat16)
@@ -109,13 +117,23 @@ def conv2d(srcs, weight, c_out, *, ksize=3, stride=1, pad_lo=1, shortcut=(), bia
     d.act, d.out, d.out_pitch, d.out_fp32, d.force_bn = act, out.data_ptr(), op, int(out_fp32), force_bn
     d.force_direct_epilogue = int(direct_epilogue)
     d.pair_mode = 0 if pair is None else (1 if pair else 2)  # CTA pairs (cta_group::2): None = library default (on where the shape allows)
+    if rowstat is not None:
+        assert rowstat.dtype == torch.float32 and rowstat.is_contiguous() and rowstat.numel() == n * h_out * w_out * (c_out // 32) * 2
+        d.rowstat_out = rowstat.data_ptr()
+    if ln is not None:
+        stats, colsum, eps = ln
+        k_in = int(srcs[0].shape[3])
+        assert stats.dtype == torch.float32 and stats.is_contiguous() and stats.numel() == n * h_in * w_in * (k_in // 32) * 2
+        assert colsum.dtype == torch.float32 and colsum.numel() >= c_out and colsum.is_contiguous()
+        d.ln_stats, d.ln_colsum, d.ln_eps = stats.data_ptr(), colsum.data_ptr(), float(eps)
     if split_k:
         ws = splitk_workspace(srcs[0].device)
         d.splitk_ws, d.splitk_ws_bytes = ws.data_ptr(), ws.numel() * 4
     # algorithmic flops: 2 * output pixels * c_out * true reduction length (padding channels excluded)
+    # (a fused-upsample conv is credited with the 9 taps of the convolution it replaces: algorithmic work is implementation independent)
     k_true = ksize * ksize * sum(int(t.shape[3]) for t in srcs) + sum(int(t.shape[3]) for t in shortcut)
     _call("ladi_conv2d_bf16", 2.0 * n * h_out * w_out * c_out * k_true, C.byref(d), _stream(),
-          tag=f"k{ksize}s{stride} M={n * h_out * w_out} N={c_out} K={k_true} act={act}")
+          tag=f"k{ksize}s{stride}{'u' if up2x else ''} M={n * h_out * w_out} N={c_out} K={k_true} act={act}{' ln' if ln is not None else ''}{' rs' if rowstat is not None else ''}")
     return out
 
 
@@ -154,16 +172,38 @@ def attention(q, k, v, heads, scale, out=None, variant=0, trace=None):
     return out
 
 
+def attention_d512(q, k, v, scale, out=None):
+    """One head of width D = 512 (VAE mid-block AttentionBlock; 256 for the reduced-width test models): q [B, Nq, D], k/v [B, Nkv, D]
+    row-strided views -> [B, Nq, D]."""
+    B, nq, nkv, D = q.shape[0], q.shape[1], k.shape[1], q.shape[2]
+    assert D in (256, 512), "the wide single-head attention kernel is built for head widths 512 and 256"
+    for t in (q, k, v):
+        assert t.dtype == torch.bfloat16 and t.stride(2) == 1 and t.shape[2] == D
+    if out is None:
+        out = torch.empty((B, nq, D), dtype=torch.bfloat16, device=q.device)
+    d = AttnDesc()
+    d.batch, d.heads, d.nq, d.nkv = B, 1, nq, nkv
+    d.q, d.q_pitch, d.q_batch_stride = q.data_ptr(), q.stride(1), q.stride(0)
+    d.k, d.k_pitch, d.k_batch_stride = k.data_ptr(), k.stride(1), k.stride(0)
+    d.v, d.v_pitch, d.v_batch_stride = v.data_ptr(), v.stride(1), v.stride(0)
+    d.out, d.out_pitch, d.out_batch_stride = out.data_ptr(), out.stride(1), out.stride(0)
+    d.scale, d.head_dim = scale, D
+    _call("ladi_attention_d512_bf16", 4.0 * B * nq * nkv * D, C.byref(d), _stream(), tag=f"B={B} d{D} nq={nq} nkv={nkv}")
+    return out
+
+
 class GroupNormWS:
     """Per-call workspace for the two-pass GroupNorm: [n][chunks][groups][2] fp32."""
 
     def __init__(self, device):
-        self.device, self.buf = device, None
+        self.device, self.buf, self._retired = device, None, []
 
     def get(self, n, hw, groups):
         need = n * lib.load().ladi_groupnorm_chunks(hw) * groups * 2
         if self.buf is None or self.buf.numel() < need:
-            self.buf = torch.empty(need, dtype=torch.float32, device=self.device)
+            if self.buf is not None:
+                self._retired.append(self.buf)  # an earlier, smaller session's captured graph still reads/writes this address
+            self.buf = torch.empty(max(need, 1 << 20), dtype=torch.float32, device=self.device)
         return self.buf
 
 
@@ -272,11 +312,21 @@ def bilinear_down8(x):
     return out
 
 
-def ddim_cfg_step(eps, latents, unet_in, cfg, guidance, coef, step_ptr, advance=True):
+def ddim_cfg_step(eps, latents, unet_in, cfg, guidance, coef, step_ptr, advance=True, noise=None):
+    """coef fp32 [steps, 8] (scheduler.coefficients); noise: NCHW fp32 variance noise of the eta > 0 update, or None."""
     B, _, h, w = latents.shape
     assert eps.dtype == torch.float32 and latents.dtype == torch.float32 and latents.is_contiguous()
+    assert coef.dtype == torch.float32 and coef.shape[-1] == 8 and coef.is_contiguous()
+    assert noise is None or (noise.dtype == torch.float32 and noise.is_contiguous() and noise.shape == latents.shape)
     lib.call("ladi_ddim_cfg_step", _ptr(eps), eps.stride(2), _ptr(latents), _ptr(unet_in), unet_in.stride(2), B, h, w, int(cfg),
-             float(guidance), _ptr(coef), _ptr(step_ptr), int(advance), _stream())
+             float(guidance), _ptr(coef), _ptr(step_ptr), int(advance), _ptr(noise), _stream())
+
+
+def check_binarise_(image, mask, flags):
+    """Range checks of prepare_mask_and_masked_image recorded in `flags` (device int32[2]) + in-place mask binarisation, no host sync."""
+    assert image.dtype == torch.float32 and mask.dtype == torch.float32 and image.is_contiguous() and mask.is_contiguous()
+    assert flags.dtype == torch.int32 and flags.numel() >= 2
+    lib.call("ladi_check_binarise", _ptr(image), image.numel(), _ptr(mask), mask.numel(), _ptr(flags), _stream())
 
 
 def image_out(x):

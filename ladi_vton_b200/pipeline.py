@@ -24,21 +24,49 @@ class StableDiffusionPipelineOutput:
 
 
 def _randn(shape, generator, device):
-    """diffusers.utils.randn_tensor: sample on the generator's device, then move."""
+    """diffusers.utils.randn_tensor: sample on the generator's device, then move.  A LIST of generators
+    (one per sample) draws every sample's (1, ...) slice from its own generator, as randn_tensor's list branch does."""
+    if isinstance(generator, (list, tuple)):
+        if len(generator) == 1:
+            generator = generator[0]
+        else:
+            if len(generator) != shape[0]:
+                raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an effective batch"
+                                 f" size of {shape[0]}. Make sure the batch size matches the length of the generators.")
+            return torch.cat([torch.randn((1,) + tuple(shape[1:]), generator=g, device=g.device, dtype=torch.float32).to(device)
+                              for g in generator], dim=0)
     gdev = generator.device if generator is not None else device
     return torch.randn(shape, generator=generator, device=gdev, dtype=torch.float32).to(device)
 
 
 class _Session:
-    """Persistent device buffers + the captured step graph for one (B, h, w, cfg) shape."""
+    """Everything one (batch, size, conditioning layout) shape needs to be replayable: static input buffers, the persistent UNet input /
+    latents / step counter, and three captured CUDA graphs -- `pre` (mask + pose preprocessing, VAE encode x2, posterior samples, EMASC,
+    UNet input assembly, text K/V), `step` (UNet forward + CFG + DDIM, replayed N times) and `post` (VAE decode with the EMASC skips +
+    image conversion)."""
 
-    def __init__(self, B, Bp, h, w, in_pitch, device):
+    def __init__(self, B, Bp, h, w, H, W, in_pitch, n_pose, ctx_shape, kv_total, device):
+        f32 = dict(dtype=torch.float32, device=device)
+        self.image = torch.zeros((B, 3, H, W), **f32)
+        self.mask = torch.zeros((B, 1, H, W), **f32)
+        self.pose = torch.zeros((B, n_pose, H, W), **f32)
+        self.cloth = torch.zeros((B, 3, H, W), **f32)
+        self.noise = [torch.zeros((B, 4, h, w), **f32) for _ in range(3)]  # cloth posterior, initial latents, masked-image posterior
+        self.step_noise = torch.zeros((B, 4, h, w), **f32)                 # eta > 0: DDIM variance noise of the current step
+        self.ctx = torch.zeros(ctx_shape, dtype=torch.bfloat16, device=device)
+        self.ctx_kv = torch.zeros((ctx_shape[0], ctx_shape[1], kv_total), dtype=torch.bfloat16, device=device)
+        self.flags = torch.zeros(2, dtype=torch.int32, device=device)
         self.unet_in = torch.zeros((Bp, h, w, in_pitch), dtype=torch.bfloat16, device=device)
-        self.latents = torch.zeros((B, 4, h, w), dtype=torch.float32, device=device)
+        self.latents = torch.zeros((B, 4, h, w), **f32)
         self.step = torch.zeros(2, dtype=torch.int32, device=device)
         self.coef = None
-        self.graph = None
-        self.guidance = None
+        self.inter = None          # EMASC outputs (mask_features applied), produced by `pre`, consumed by `post`
+        self.out_f32 = self.out_u8 = None
+        self.host_f32 = self.host_u8 = None  # pinned staging for the D2H of the result
+        self.calls = 0
+        self.g_pre = self.g_step = self.g_post = None
+        self.step_key = self.pre_key = self.post_key = None
+        self.step_nodes = self.pre_nodes = self.post_nodes = 0
 
 
 class StableDiffusionTryOnePipeline:
@@ -56,6 +84,7 @@ class StableDiffusionTryOnePipeline:
         self.device = torch.device("cpu")
         self.use_cuda_graph = True
         self._sessions = {}
+        self._pack_gens = None
 
     def to(self, device):
         device = torch.device(device)
@@ -144,12 +173,37 @@ class StableDiffusionTryOnePipeline:
         return prompt_embeds
 
     @staticmethod
-    def _prepare_mask_and_image(image, mask):
-        """diffusers prepare_mask_and_masked_image, tensor branch (called at tryon_pipe.py:630): shape normalisation, range
-        checks (raise ValueError) and IN-PLACE binarisation of the caller's mask at 0.5.  The `image * (mask < 0.5)` product
-        itself is fused into the layout kernel (ops.nchw_to_nhwc gate)."""
+    def _pil_to_tensors(image, mask):
+        """diffusers prepare_mask_and_masked_image, PIL / ndarray branch (called at tryon_pipe.py:630): image -> float32 [-1, 1] NCHW,
+        mask -> float32 [0, 1] N1HW.  Host-side conversion (the reference does the same with numpy)."""
+        import numpy as np
+        from PIL import Image
+        if isinstance(image, (Image.Image, np.ndarray)):
+            image = [image]
+        if isinstance(image, list) and isinstance(image[0], Image.Image):
+            image = np.concatenate([np.array(i.convert("RGB"))[None, :] for i in image], axis=0)
+        elif isinstance(image, list) and isinstance(image[0], np.ndarray):
+            image = np.concatenate([i[None, :] for i in image], axis=0)
+        image = torch.from_numpy(np.ascontiguousarray(image.transpose(0, 3, 1, 2))).to(dtype=torch.float32) / 127.5 - 1.0
+        if isinstance(mask, (Image.Image, np.ndarray)):
+            mask = [mask]
+        if isinstance(mask, list) and isinstance(mask[0], Image.Image):
+            mask = np.concatenate([np.array(m.convert("L"))[None, None, :] for m in mask], axis=0).astype(np.float32) / 255.0
+        elif isinstance(mask, list) and isinstance(mask[0], np.ndarray):
+            mask = np.concatenate([m[None, None, :] for m in mask], axis=0).astype(np.float32)
+        return image, torch.from_numpy(np.ascontiguousarray(mask))
+
+    def _prepare_mask_and_image(self, image, mask, flags):
+        """diffusers prepare_mask_and_masked_image (called at tryon_pipe.py:630): shape normalisation, the [-1,1] / [0,1] range checks and
+        the IN-PLACE binarisation of the caller's mask at 0.5.  Device tensors: one kernel, the range flags are read back with the
+        result (no host sync before the work is queued); host tensors: checked on the host, raising at once like the reference.
+        `image * (mask < 0.5)` itself is fused into the layout kernel (ops.nchw_to_nhwc gate)."""
         if not isinstance(image, torch.Tensor) or not isinstance(mask, torch.Tensor):
-            raise TypeError("`image` and `mask_image` must be torch tensors (PIL inputs are not supported by this engine)")
+            if isinstance(image, torch.Tensor) or isinstance(mask, torch.Tensor):
+                raise TypeError("`image` and `mask_image` must both be torch tensors or both PIL images / arrays")
+            if self.emasc:  # the reference hands mask_image to mask_features (tryon_pipe.py:685), which needs a tensor
+                raise TypeError("with EMASC, `mask_image` must be a torch tensor (mask_features interpolates it, src/utils/data_utils.py:9)")
+            image, mask = self._pil_to_tensors(image, mask)
         if image.ndim == 3:
             image = image.unsqueeze(0)
         if mask.ndim == 2:
@@ -159,12 +213,16 @@ class StableDiffusionTryOnePipeline:
         assert image.ndim == 4 and mask.ndim == 4, "Image and Mask must have 4 dimensions"
         assert image.shape[-2:] == mask.shape[-2:], "Image and Mask must have the same spatial dimensions"
         assert image.shape[0] == mask.shape[0], "Image and Mask must have the same batch size"
-        if image.min() < -1 or image.max() > 1:
-            raise ValueError("Image should be in [-1, 1] range")
-        if mask.min() < 0 or mask.max() > 1:
-            raise ValueError("Mask should be in [0, 1] range")
-        mask[mask < 0.5] = 0
-        mask[mask >= 0.5] = 1
+        fast = all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for t in (image, mask))
+        if fast:
+            ops.check_binarise_(image, mask, flags)
+        else:
+            if image.min() < -1 or image.max() > 1:
+                raise ValueError("Image should be in [-1, 1] range")
+            if mask.min() < 0 or mask.max() > 1:
+                raise ValueError("Mask should be in [0, 1] range")
+            mask[mask < 0.5] = 0
+            mask[mask >= 0.5] = 1
         return mask, image
 
     def numpy_to_pil(self, images):
@@ -174,10 +232,63 @@ class StableDiffusionTryOnePipeline:
         images = (images * 255).round().astype("uint8")
         return [Image.fromarray(im) for im in images]
 
-    # ---- the denoising step that gets captured --------------------------------------------------------------------------
-    def _step(self, s, cfg, guidance, advance=True):
+    # ---- the three captured pieces of one call ----------------------------------------------------------------------------
+    def _pre(self, s, lay):
+        """Steps 4-7a of tryon_pipe.py:629-705 on the session's static buffers."""
+        B, cfg, vsf, sf = lay["B"], lay["cfg"], self.vae_scale_factor, self.vae.config.scaling_factor
+        s.unet_in.zero_()
+        cond = s.unet_in[B:] if cfg else s.unet_in  # conditional half of the CFG batch ([uncond, cond], tryon_pipe.py:315,702-705)
+        if not lay["no_pose"]:
+            ops.nchw_to_nhwc(ops.bilinear_down8(s.pose), cond, c_off=lay["c_pose"])  # :632-634
+        if lay["cloth"]:  # 4b. warped cloth latents (RNG draw #1)
+            mom, _ = self.vae.encode_nhwc(s.cloth)
+            ops.nchw_to_nhwc(ops.posterior_sample(mom, s.noise[0], sf), cond, c_off=lay["c_cloth"])
+        s.latents.copy_(s.noise[1])  # 6. latents (RNG draw #2, already times init_noise_sigma)
+        # 7. masked image -> latents + encoder skips (RNG draw #3); EMASC with mask_features fused
+        H, W = s.image.shape[2], s.image.shape[3]
+        masked = torch.zeros((B, H, W, 8), dtype=torch.bfloat16, device=self.device)
+        ops.nchw_to_nhwc(s.image, masked, gate=s.mask)  # image * (mask < 0.5)
+        mom, feats = self.vae.encode_nhwc(masked, nhwc=True)
+        masked_lat = ops.posterior_sample(mom, s.noise[2], sf)
+        s.inter = None
+        if self.emasc:
+            sel = [feats[i] for i in self.emasc_int_layers]  # :460-461
+            inv = [ops.inv_mask_rows(s.mask, H // f.shape[1]) for f in sel]  # data_utils.py:9-14 (chained nearest == direct)
+            s.inter = self.emasc(sel, inv)  # :684-685
+        for half in ((s.unet_in[:B], s.unet_in[B:]) if cfg else (s.unet_in,)):  # :482-485
+            ops.nchw_to_nhwc(s.mask, half, c_off=lay["c_mask"], f=vsf)  # nearest /8 (:434-436)
+            ops.nchw_to_nhwc(masked_lat, half, c_off=lay["c_masked"])
+            ops.nchw_to_nhwc(s.latents, half, c_off=0)
+        self.unet.plan_context(s.ctx, out=s.ctx_kv)  # step-invariant: text K/V of all 16 cross-attention layers
+        s.step.zero_()
+
+    def _step(self, s, cfg, guidance, eta_noise=False, advance=True):
         eps = self.unet.forward_nhwc(s.unet_in, s.step)
-        ops.ddim_cfg_step(eps, s.latents, s.unet_in, cfg, guidance, s.coef, s.step, advance=advance)
+        ops.ddim_cfg_step(eps, s.latents, s.unet_in, cfg, guidance, s.coef, s.step, advance=advance, noise=s.step_noise if eta_noise else None)
+
+    def _post(self, s, lay):
+        """decode_latents (tryon_pipe.py:349-359) with the EMASC skips, then both image conversions (fp32 [0,1] and numpy_to_pil's uint8)."""
+        sf = self.vae.config.scaling_factor
+        img = self.vae.decode_nhwc(s.latents, s.inter, self.emasc_int_layers if s.inter is not None else None, scale=1.0 / sf)
+        s.out_f32 = ops.image_out(img)     # [B, H, W, 3] fp32 in [0, 1]  (:356)
+        s.out_u8 = ops.image_out_u8(img)   # (x * 255).round().astype(uint8)  (:760)
+
+    def _run(self, s, which, fn, key, use_graph):
+        """Run one of the three pieces eagerly (first call of a shape = warm-up, or graphs off) or as a captured graph."""
+        g_attr, k_attr, n_attr = f"g_{which}", f"{which}_key", f"{which}_nodes"
+        if not use_graph:
+            return fn()
+        if getattr(s, g_attr) is None or getattr(s, k_attr) != key:
+            g = torch.cuda.CUDAGraph()
+            n0 = lib.launches
+            with torch.cuda.graph(g):
+                fn()
+            setattr(s, n_attr, lib.launches - n0)
+            lib.launches = n0  # capture records, it does not launch
+            setattr(s, g_attr, g)
+            setattr(s, k_attr, key)
+        getattr(s, g_attr).replay()
+        lib.launches += getattr(s, n_attr)
 
     @torch.no_grad()
     def __call__(self, image, mask_image, pose_map, warped_cloth, prompt=None, height=None, width=None,
@@ -198,12 +309,13 @@ class StableDiffusionTryOnePipeline:
             raise ValueError("`image` input cannot be undefined.")
         if mask_image is None:
             raise ValueError("`mask_image` input cannot be undefined.")
-        if eta != 0.0:
-            raise NotImplementedError("eta != 0 (stochastic DDIM) is never used by the reference CLI and is not implemented")
-        if isinstance(generator, list):
-            raise NotImplementedError("per-sample generator lists are not supported; pass one generator")
         if cloth_input_type not in ("warped", "none"):
             raise ValueError(f"Invalid cloth_input_type {cloth_input_type}")
+        if num_images_per_prompt != 1:
+            # the reference accepts the argument but its own body then concatenates [B*num, ...] latents with [B, ...] pose / cloth
+            # tensors (tryon_pipe.py:702-726) and fails inside torch.cat; say so instead of failing somewhere in a kernel wrapper
+            raise ValueError("num_images_per_prompt != 1 is not supported by the try-on pipeline: pose_map / warped_cloth are not repeated "
+                             "to the effective batch (the reference fails in torch.cat at tryon_pipe.py:724); repeat the inputs instead")
         if prompt is not None:
             batch_size = 1 if isinstance(prompt, str) else len(prompt)
         else:
@@ -212,105 +324,104 @@ class StableDiffusionTryOnePipeline:
         ctx = self._encode_prompt(prompt, dev, num_images_per_prompt, cfg, negative_prompt, prompt_embeds, negative_prompt_embeds)
         B = batch_size * num_images_per_prompt
         Bp = 2 * B if cfg else B
-        sf = self.vae.config.scaling_factor
         vsf = self.vae_scale_factor
         h, w = height // vsf, width // vsf
+        if isinstance(generator, (list, tuple)) and len(generator) != 1 and len(generator) != B:  # prepare_latents :412-416
+            raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an effective batch"
+                             f" size of {B}. Make sure the batch size matches the length of the generators.")
 
-        # 4. mask / image / pose preprocessing (validation on the tensors' own device, compute in fused layout kernels)
-        mask, image = self._prepare_mask_and_image(image, mask_image)
-        mask_d = mask.to(dev, torch.float32).contiguous()
-        image_d = image.to(dev, torch.float32).contiguous()
+        # ---- session (static buffers + graphs) for this shape / conditioning layout
+        n_pose = pose_map.shape[1]
         cin = self.unet.config.in_channels
-        key = (B, Bp, h, w)
+        lay = dict(B=B, cfg=cfg, no_pose=bool(no_pose), cloth=cloth_input_type == "warped", c_mask=4, c_masked=5, c_pose=9, c_cloth=9 + n_pose)
+        assert cin == lay["c_cloth"] + (4 if lay["cloth"] else 0), "UNet in_channels does not match the conditioning"
+        gens = (self.unet.pack_gen, self.vae.pack_gen, self.emasc.pack_gen if self.emasc else 0)
+        if gens != self._pack_gens:  # weights were re-packed: every captured graph points at freed memory
+            self._sessions.clear()
+            self._pack_gens = gens
+        key = (B, Bp, h, w, n_pose, lay["no_pose"], lay["cloth"], bool(self.emasc), tuple(ctx.shape[1:]))
         s = self._sessions.get(key)
         if s is None:
-            s = self._sessions[key] = _Session(B, Bp, h, w, self.unet.in_pitch, dev)
-        s.unet_in.zero_()
-        n_pose = pose_map.shape[1]
-        c_mask, c_masked, c_pose, c_cloth = 4, 5, 9, 9 + n_pose
-        assert cin == c_cloth + (4 if cloth_input_type == "warped" else 0), "UNet in_channels does not match the conditioning"
-        cond = s.unet_in[B:] if cfg else s.unet_in  # conditional half of the CFG batch ([uncond, cond], tryon_pipe.py:315,702-705)
-        if not no_pose:
-            pose_d = ops.bilinear_down8(pose_map.to(dev, torch.float32).contiguous())  # :632-634
-            ops.nchw_to_nhwc(pose_d, cond, c_off=c_pose)
-        # 4b. warped cloth latents (RNG draw #1)
-        if cloth_input_type == "warped":
-            mom, _ = self.vae.encode_nhwc(warped_cloth)
-            cloth = ops.posterior_sample(mom, noise[0].to(dev) if noise is not None else _randn((B, 4, h, w), generator, dev), sf)
-            ops.nchw_to_nhwc(cloth, cond, c_off=c_cloth)
-        # 5. timesteps, 6. latents (RNG draw #2)
+            s = self._sessions[key] = _Session(B, Bp, h, w, height, width, self.unet.in_pitch, n_pose, tuple(ctx.shape), self.unet.kv_total, dev)
+        use_graph = self.use_cuda_graph and s.calls > 0  # the first call of a shape runs eagerly: lazy kernel attributes, allocations
+
+        # 4. mask / image validation + in-place binarisation (flags read back with the result), inputs -> static buffers
+        s.flags.zero_()
+        mask, image = self._prepare_mask_and_image(image, mask_image, s.flags)
+        s.image.copy_(image, non_blocking=True)
+        s.mask.copy_(mask, non_blocking=True)
+        if not lay["no_pose"]:
+            s.pose.copy_(pose_map, non_blocking=True)
+        s.ctx.copy_(ctx, non_blocking=True)
+        # RNG draws in the reference's order: cloth posterior (:640), initial latents (:419), masked-image posterior (:458)
+        if lay["cloth"]:
+            s.cloth.copy_(warped_cloth, non_blocking=True)
+            s.noise[0].copy_(noise[0] if noise is not None else _randn((B, 4, h, w), generator, dev), non_blocking=True)
+        # 5. timesteps
         self.scheduler.set_timesteps(num_inference_steps, device=dev)
         ts = self.scheduler.timesteps_host
         cloth_steps = (1 - cloth_cond_rate) * num_inference_steps
         if latents is None:
             latents = noise[1] if noise is not None else _randn((B, 4, h, w), generator, dev)
-        s.latents.copy_(latents.to(dev, torch.float32) * self.scheduler.init_noise_sigma)
-        # 7. masked image -> latents + encoder skips (RNG draw #3); EMASC with mask_features fused
-        masked = torch.zeros((B, height, width, 8), dtype=torch.bfloat16, device=dev)
-        ops.nchw_to_nhwc(image_d, masked, gate=mask_d)  # image * (mask < 0.5)
-        mom, feats = self.vae.encode_nhwc(masked, nhwc=True)
-        masked_lat = ops.posterior_sample(mom, noise[2].to(dev) if noise is not None else _randn((B, 4, h, w), generator, dev), sf)
-        inter = None
-        if self.emasc:
-            sel = [feats[i] for i in self.emasc_int_layers]  # :460-461
-            inv = [ops.inv_mask_rows(mask_d, height // f.shape[1]) for f in sel]  # data_utils.py:9-14 (chained nearest == direct)
-            inter = self.emasc(sel, inv)  # :684-685
-        for half in ((s.unet_in[:B], s.unet_in[B:]) if cfg else (s.unet_in,)):  # :482-485
-            ops.nchw_to_nhwc(mask_d, half, c_off=c_mask, f=vsf)  # nearest /8 (:434-436)
-            ops.nchw_to_nhwc(masked_lat, half, c_off=c_masked)
-            ops.nchw_to_nhwc(s.latents, half, c_off=0)
-        # step-invariant UNet work
-        self.unet.plan_context(ctx)
+        s.noise[1].copy_(latents.to(dev, torch.float32) * self.scheduler.init_noise_sigma, non_blocking=True)
+        s.noise[2].copy_(noise[2] if noise is not None else _randn((B, 4, h, w), generator, dev), non_blocking=True)
+        self._run(s, "pre", lambda: self._pre(s, lay), (self.unet.ws.buf.data_ptr() if self.unet.ws.buf is not None else 0,
+                                                       self.vae.ws.buf.data_ptr() if self.vae.ws.buf is not None else 0), use_graph)
+        self.unet._ctx = s.ctx_kv  # (a replayed `pre` graph did not run plan_context's Python)
+        # step-invariant UNet tables
         self.unet.plan_steps(ts)
-        coef = self.scheduler.coefficients()
+        coef = self.scheduler.coefficients(eta=eta)
         if s.coef is None or s.coef.shape != coef.shape:
             s.coef = coef.to(dev)
         else:
-            s.coef.copy_(coef)
-        s.step.zero_()
+            s.coef.copy_(coef, non_blocking=True)
         # 9. denoising loop
         n_zero_from = num_inference_steps - cloth_steps  # :718-719
-        use_graph = self.use_cuda_graph and callback is None
+        stochastic = eta > 0
+        step_graph = self.use_cuda_graph and callback is None
+        step_key = self._graph_key() + (s.coef.data_ptr(), float(guidance_scale), stochastic)
         for i in range(num_inference_steps):
-            if cloth_input_type == "warped" and i >= n_zero_from and cloth_steps > 0:
-                s.unet_in[..., c_cloth:c_cloth + 4].zero_()
-            stale = s.graph is None or s.guidance != guidance_scale or s.graph_key != self._graph_key() + (s.coef.data_ptr(),)
-            if not use_graph or (i == 0 and stale):
-                self._step(s, cfg, guidance_scale)  # first step of a new shape runs eagerly: the warm-up before capture
+            if lay["cloth"] and i >= n_zero_from and cloth_steps > 0:
+                s.unet_in[..., lay["c_cloth"]:lay["c_cloth"] + 4].zero_()
+            if stochastic:  # DDIMScheduler.step draws randn_tensor(model_output.shape, generator=...) once per step (after the 3 initial draws)
+                s.step_noise.copy_(_randn((B, 4, h, w), generator, dev), non_blocking=True)
+            stale = s.g_step is None or s.step_key != step_key
+            if not step_graph or (i == 0 and stale):
+                self._step(s, cfg, guidance_scale, stochastic)  # first step of a new shape runs eagerly: the warm-up before capture
             else:
-                if stale:
-                    s.graph = torch.cuda.CUDAGraph()
-                    n0 = lib.launches
-                    with torch.cuda.graph(s.graph):
-                        self._step(s, cfg, guidance_scale)
-                    s.graph_nodes = lib.launches - n0
-                    lib.launches = n0  # capture records, it does not launch
-                    s.guidance, s.graph_key = guidance_scale, self._graph_key() + (s.coef.data_ptr(),)
-                    # capture records but does not execute: fall through to the replay below
-                s.graph.replay()
-                lib.launches += s.graph_nodes
+                self._run(s, "step", lambda: self._step(s, cfg, guidance_scale, stochastic), step_key, True)
             if callback is not None and i % callback_steps == 0:
                 callback(i, ts[i], s.latents)
         # 11. decode with the EMASC skips, clamp, D2H
-        img = self.vae.decode_nhwc(s.latents, inter, self.emasc_int_layers if inter is not None else None, scale=1.0 / sf)
-        if output_type == "pil":  # numpy_to_pil's (x*255).round().astype(uint8) on the device: a quarter of the D2H bytes (:358-760)
-            from PIL import Image
-            u8 = ops.image_out_u8(img).cpu().numpy()
-            pil = [Image.fromarray(im) for im in u8]
-            return StableDiffusionPipelineOutput(images=pil, nsfw_content_detected=None) if return_dict else (pil, None)
-        out = ops.image_out(img)  # [B, H, W, 3] fp32 in [0, 1]  (:356)
-        if output_type == "pt":  # extension: leave the result on the device (used for device-resident timing / NCCL gather)
+        post_key = (self.vae.ws.buf.data_ptr() if self.vae.ws.buf is not None else 0,) + tuple(t.data_ptr() for t in (s.inter or ()))
+        self._run(s, "post", lambda: self._post(s, lay), post_key, use_graph)
+        s.calls += 1
+        if output_type in ("pt", "pt_u8"):  # extensions: leave the result on the device (fp32 [0,1] / numpy_to_pil's uint8) for device-resident
+            out = (s.out_f32 if output_type == "pt" else s.out_u8).clone()  # timing and the NCCL gather; the range flags stay unchecked
             return StableDiffusionPipelineOutput(images=out, nsfw_content_detected=None) if return_dict else (out, None)
-        out = out.cpu().numpy()  # (:358)
+        if output_type == "pil":  # numpy_to_pil's uint8 conversion already happened on the device: a quarter of the D2H bytes (:358-760)
+            if s.host_u8 is None:
+                s.host_u8 = torch.empty(s.out_u8.shape, dtype=torch.uint8, pin_memory=True)
+            s.host_u8.copy_(s.out_u8, non_blocking=True)
+        else:
+            if s.host_f32 is None:
+                s.host_f32 = torch.empty(s.out_f32.shape, dtype=torch.float32, pin_memory=True)
+            s.host_f32.copy_(s.out_f32, non_blocking=True)
+        flags = s.flags.cpu()  # synchronises the stream: the pinned result above is complete too
+        if int(flags[0]):
+            raise ValueError("Image should be in [-1, 1] range")
+        if int(flags[1]):
+            raise ValueError("Mask should be in [0, 1] range")
         if output_type == "pil":
-            out = self.numpy_to_pil(out)
+            from PIL import Image
+            out = [Image.fromarray(im) for im in s.host_u8.numpy().copy()]
+        else:
+            out = s.host_f32.numpy().copy()  # (:358) the staging buffer is reused by the next call
         if not return_dict:
             return (out, None)
         return StableDiffusionPipelineOutput(images=out, nsfw_content_detected=None)
 
     def _graph_key(self):
-        # the captured graph bakes in the addresses of the planned step table / text K/V buffers
-        return (self.unet._steps.data_ptr(), self.unet._ctx.data_ptr(), self.unet._steps.shape[0])
-
-    def _coef_ptr(self, s):
-        return s.coef.data_ptr()
+        # the captured step graph bakes in the addresses of the planned step table, the text K/V buffer and the GroupNorm workspace
+        ws = self.unet.ws.buf
+        return (self.unet._steps.data_ptr(), self.unet._ctx.data_ptr(), self.unet._steps.shape[0], ws.data_ptr() if ws is not None else 0)

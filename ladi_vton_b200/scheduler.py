@@ -49,28 +49,34 @@ class DDIMScheduler:
     def scale_model_input(self, sample, timestep=None):
         return sample
 
-    def coefficients(self, timesteps=None):
-        """fp32 [steps, 4] = {1/sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev)} (eta = 0)."""
+    def coefficients(self, timesteps=None, eta=0.0):
+        """fp32 [steps, 8] = {1/sqrt(a_t), sqrt(1-a_t), sqrt(a_prev), sqrt(1-a_prev-sigma_t^2), sigma_t, 0, 0, 0} with DDIM's
+        sigma_t = eta * sqrt((1-a_prev)/(1-a_t) * (1 - a_t/a_prev))  (DDIMScheduler._get_variance / step; 0 for the CLI's eta = 0)."""
         timesteps = self.timesteps_host if timesteps is None else timesteps
         ratio = self.config.num_train_timesteps // self.num_inference_steps
         rows = []
+        zero = torch.tensor(0.0)
         for t in timesteps:
             tp = t - ratio
             a_t = self.alphas_cumprod[t]
             a_p = self.alphas_cumprod[tp] if tp >= 0 else self.final_alpha_cumprod
-            rows.append(torch.stack([1.0 / a_t ** 0.5, (1 - a_t) ** 0.5, a_p ** 0.5, (1 - a_p) ** 0.5]))
+            var = (1 - a_p) / (1 - a_t) * (1 - a_t / a_p)
+            sigma = eta * var ** 0.5
+            rows.append(torch.stack([1.0 / a_t ** 0.5, (1 - a_t) ** 0.5, a_p ** 0.5, (1 - a_p - sigma ** 2) ** 0.5, sigma + zero, zero, zero, zero]))
         return torch.stack(rows).to(torch.float32)
 
     def step(self, model_output, timestep, sample, eta=0.0, generator=None, return_dict=True):
         """Generic one-step API (NCHW tensors on the CUDA device), kept for signature parity (tryon_pipe.py:337-345
         introspects `eta`/`generator`); the pipeline itself calls the fused kernel directly."""
-        if eta != 0.0:
-            raise NotImplementedError("eta != 0 is never used by the reference CLI")
         dev = sample.device
-        coef = self.coefficients([int(timestep)]).to(dev)
+        coef = self.coefficients([int(timestep)], eta=eta).to(dev)
         B, c, h, w = sample.shape
         eps = model_output.float().permute(0, 2, 3, 1).contiguous()
         lat = sample.float().contiguous().clone()
         scratch = torch.empty((B, h, w, 8), dtype=torch.bfloat16, device=dev)
-        ops.ddim_cfg_step(eps, lat, scratch, False, 1.0, coef, None, advance=False)
+        noise = None
+        if eta > 0:  # variance noise drawn like diffusers' randn_tensor(model_output.shape, generator=generator, device=...)
+            gdev = generator.device if generator is not None else dev
+            noise = torch.randn(tuple(model_output.shape), generator=generator, device=gdev, dtype=torch.float32).to(dev).contiguous()
+        ops.ddim_cfg_step(eps, lat, scratch, False, 1.0, coef, None, advance=False, noise=noise)
         return _Step(lat.to(sample.dtype))

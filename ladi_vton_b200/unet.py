@@ -10,14 +10,22 @@ Appendix A.7), `unet(x_nchw, t, encoder_hidden_states=ctx).sample`.  Internally 
     `plan_steps` tabulates `conv1.bias + time_emb_proj(...)` once per call and conv1's epilogue indexes it with the
     device-side step counter (graph-replay friendly);
   * cross-attention K/V of the text context are step-invariant: one GEMM per call for all 16 layers (`plan_context`);
-  * attention: fused flash kernel reading per-head slices of the fused QKV projection in place.
+  * attention: fused flash kernel reading per-head slices of the fused QKV projection in place;
+  * LayerNorm (norm1/2/3 of every BasicTransformerBlock) never runs as a pass: the GEMM that produces the tensor also emits per-row
+    partial sums, the GEMM that consumes it multiplies the raw tensor with W diag(gamma) and applies mean/rstd as a rank-1 correction
+    in its epilogue (weights.fold_layernorm; env LADI_LN_FOLD=0 packs the stand-alone form for A/B timing);
+  * Upsample2D: nearest-2x + conv3x3 as ONE sub-pixel convolution over the half-resolution tensor (4/9 of the MACs, no intermediate;
+    env LADI_UP2X=0 for the materialised form).
 """
 import math
+import os
 
 import torch
 
 from . import ops
-from .weights import f32, interleave_geglu, pack_conv, pack_linear
+from .weights import f32, fold_layernorm, interleave_geglu, pack_conv, pack_conv_up2x, pack_linear
+
+LN_EPS = 1e-5  # nn.LayerNorm default (BasicTransformerBlock.norm1/2/3)
 
 SD2_INPAINT_UNET = dict(
     in_channels=31, out_channels=4, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2,
@@ -115,7 +123,9 @@ class UNet2DConditionModel:
         self._sd = None
         self.P = None
         self._steps = None
+        self._steps_key = None
         self._ctx = None
+        self.pack_gen = 0  # bumped by every re-pack: captured graphs hold the packed weights' addresses (pipeline._graph_key)
 
     # ---- reference-compatible surface -------------------------------------------------------------------------------
     def eval(self):
@@ -147,9 +157,13 @@ class UNet2DConditionModel:
             device = torch.device(device)
             if device.type != "cuda":
                 raise RuntimeError("ladi_vton_b200 UNet runs on CUDA (sm_100a) only; there is no CPU path")
+            if self.P is not None and device == self.device:
+                return self  # already packed on this device: re-packing would free weights a captured graph still points at
             self.device = device
             if self._sd is not None:
                 self._pack()
+            elif self.P is not None:
+                raise RuntimeError("the state dict was released after packing; call load_state_dict again to move the UNet")
         return self
 
     def __call__(self, sample, timestep, encoder_hidden_states, return_dict=True):
@@ -173,6 +187,8 @@ class UNet2DConditionModel:
         ch, L = cfg.block_out_channels, cfg.layers_per_block
         self.in_pitch = (cfg.in_channels + 7) // 8 * 8
         self.resnets, self.transformers = [], []
+        self.fold_ln = os.environ.get("LADI_LN_FOLD", "1") != "0"
+        self.fuse_up = os.environ.get("LADI_UP2X", "1") != "0"
 
         def conv(p, srcs):
             P[p + ".w"] = pack_conv(g(p + ".weight"), srcs)
@@ -196,14 +212,20 @@ class UNet2DConditionModel:
             P[p + ".norm"] = (f32(g(p + ".norm.weight")), f32(g(p + ".norm.bias")))
             for n in ("proj_in", "proj_out"):
                 P[p + f".{n}.w"], P[p + f".{n}.b"] = pack_linear(g(p + f".{n}.weight")), f32(g(p + f".{n}.bias"))
-            for i in (1, 2, 3):
-                P[b + f".ln{i}"] = (f32(g(b + f".norm{i}.weight")), f32(g(b + f".norm{i}.bias")))
-            P[b + ".qkv"] = pack_linear(torch.cat([g(b + ".attn1.to_q.weight"), g(b + ".attn1.to_k.weight"), g(b + ".attn1.to_v.weight")]))
-            P[b + ".o1.w"], P[b + ".o1.b"] = pack_linear(g(b + ".attn1.to_out.0.weight")), f32(g(b + ".attn1.to_out.0.bias"))
-            P[b + ".q2"] = pack_linear(g(b + ".attn2.to_q.weight"))
-            P[b + ".o2.w"], P[b + ".o2.b"] = pack_linear(g(b + ".attn2.to_out.0.weight")), f32(g(b + ".attn2.to_out.0.bias"))
+            wqkv = torch.cat([g(b + ".attn1.to_q.weight"), g(b + ".attn1.to_k.weight"), g(b + ".attn1.to_v.weight")])
             wi, bi = interleave_geglu(g(b + ".ff.net.0.proj.weight"), g(b + ".ff.net.0.proj.bias"))
-            P[b + ".ff1.w"], P[b + ".ff1.b"] = pack_linear(wi), f32(bi)
+            if self.fold_ln and c % 64 == 0:  # LayerNorm folded into its consumer: (W diag(gamma), colsum, W beta + bias)
+                ln = lambda i: (g(b + f".norm{i}.weight"), g(b + f".norm{i}.bias"))
+                P[b + ".qkv"], P[b + ".qkv.cs"], P[b + ".qkv.b"] = fold_layernorm(wqkv, *ln(1))
+                P[b + ".q2"], P[b + ".q2.cs"], P[b + ".q2.b"] = fold_layernorm(g(b + ".attn2.to_q.weight"), *ln(2))
+                P[b + ".ff1.w"], P[b + ".ff1.cs"], P[b + ".ff1.b"] = fold_layernorm(wi, *ln(3), bi)
+            else:
+                for i in (1, 2, 3):
+                    P[b + f".ln{i}"] = (f32(g(b + f".norm{i}.weight")), f32(g(b + f".norm{i}.bias")))
+                P[b + ".qkv"], P[b + ".q2"] = pack_linear(wqkv), pack_linear(g(b + ".attn2.to_q.weight"))
+                P[b + ".ff1.w"], P[b + ".ff1.b"] = pack_linear(wi), f32(bi)
+            P[b + ".o1.w"], P[b + ".o1.b"] = pack_linear(g(b + ".attn1.to_out.0.weight")), f32(g(b + ".attn1.to_out.0.bias"))
+            P[b + ".o2.w"], P[b + ".o2.b"] = pack_linear(g(b + ".attn2.to_out.0.weight")), f32(g(b + ".attn2.to_out.0.bias"))
             P[b + ".ff2.w"], P[b + ".ff2.b"] = pack_linear(g(b + ".ff.net.2.weight")), f32(g(b + ".ff.net.2.bias"))
             self.transformers.append((p, c))
 
@@ -230,11 +252,17 @@ class UNet2DConditionModel:
                 if t.startswith("CrossAttn"):
                     transformer(f"up_blocks.{i}.attentions.{l}", out)
             if i < len(ch) - 1:
-                conv(f"up_blocks.{i}.upsamplers.0.conv", [out])
+                p = f"up_blocks.{i}.upsamplers.0.conv"
+                if self.fuse_up:
+                    P[p + ".w"], P[p + ".b"] = pack_conv_up2x(g(p + ".weight"), [out]), f32(g(p + ".bias"))
+                else:
+                    conv(p, [out])
         P["conv_norm_out"] = (f32(g("conv_norm_out.weight")), f32(g("conv_norm_out.bias")))
         conv("conv_out", [ch[0]])
         # time-embedding MLP + one fused projection for all resnets: rows = [time_emb_proj_r ; ...], bias += conv1.bias
-        P["te1.w"], P["te1.b"] = pack_linear(g("time_embedding.linear_1.weight")), f32(g("time_embedding.linear_1.bias"))
+        # linear_1 reads the fp32 sinusoid table as a (hi, lo) pair of bf16 columns against [W | W]: input error 2^-17 instead of 2^-9
+        w1 = g("time_embedding.linear_1.weight")
+        P["te1.w"], P["te1.b"] = pack_linear(torch.cat([pack_linear(w1).float(), pack_linear(w1).float()], dim=1)), f32(g("time_embedding.linear_1.bias"))
         P["te2.w"], P["te2.b"] = pack_linear(g("time_embedding.linear_2.weight")), f32(g("time_embedding.linear_2.bias"))
         P["temb_all.w"] = pack_linear(torch.cat([g(p + ".time_emb_proj.weight") for p, _ in self.resnets]))
         P["temb_all.b"] = f32(torch.cat([g(p + ".time_emb_proj.bias") + g(p + ".conv1.bias") for p, _ in self.resnets]))
@@ -253,29 +281,43 @@ class UNet2DConditionModel:
         self.kv_total = off
         self.P = P
         self.ws = ops.GroupNormWS(dev)
-        self._sd_keep = None
+        self.pack_gen += 1
+        self._steps = self._steps_key = self._ctx = None
+        if any(v.is_cuda for v in sd.values()):
+            self._sd = None  # device-resident fp32 source weights (3.5 GB for the full UNet) are not kept beside the bf16 pack
 
     # ---- per-call planning (step-invariant work) ----------------------------------------------------
     def plan_steps(self, timesteps):
         """Tabulate conv1.bias + time_emb_proj(silu(time_embedding(t))) for every step: fp32 [steps, sum C_out]."""
         P, c0 = self.P, self.config.block_out_channels[0]
+        key = tuple(int(x) for x in timesteps)
+        if self._steps is not None and self._steps_key == key:
+            return self._steps  # same schedule as the previous call: the table (and its address) stands
         half = c0 // 2
         t = torch.tensor([float(x) for x in timesteps], dtype=torch.float32)
         freq = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
         arg = t[:, None] * freq[None, :]
-        emb = torch.cat([torch.cos(arg), torch.sin(arg)], dim=-1).to(self.device, torch.bfloat16)  # input table (host-side)
-        e1 = ops.gemm(emb, P["te1.w"], P["te1.w"].shape[0], bias=P["te1.b"], act=ops.ACT_SILU)
+        emb = torch.cat([torch.cos(arg), torch.sin(arg)], dim=-1)  # fp32 input table (host-side)
+        kp = P["te1.w"].shape[1] // 2
+        hi = emb.to(torch.bfloat16)
+        lo = (emb - hi.float()).to(torch.bfloat16)
+        pair = torch.zeros((emb.shape[0], 2 * kp), dtype=torch.bfloat16)
+        pair[:, :c0], pair[:, kp:kp + c0] = hi, lo
+        e1 = ops.gemm(pair.to(self.device), P["te1.w"], P["te1.w"].shape[0], bias=P["te1.b"], act=ops.ACT_SILU)
         e2 = ops.gemm(e1, P["te2.w"], P["te2.w"].shape[0], bias=P["te2.b"], act=ops.ACT_SILU)  # = silu(emb)
         keep = self._steps if (self._steps is not None and tuple(self._steps.shape) == (len(timesteps), self.temb_total)) else None
         self._steps = ops.gemm(e2, P["temb_all.w"], self.temb_total, bias=P["temb_all.b"], out_fp32=True, out=keep)  # stable address
+        self._steps_key = key
         return self._steps
 
-    def plan_context(self, ctx):
-        """K/V of the text context for all 16 cross-attention layers: bf16 [B', 77, sum 2C]."""
+    def plan_context(self, ctx, out=None):
+        """K/V of the text context for all 16 cross-attention layers: bf16 [B', 77, sum 2C].  `out`: caller-owned buffer (the pipeline
+        keeps one per session so captured graphs of different shapes never share or invalidate it)."""
         B, T, D = ctx.shape
         c = ctx.to(self.device, torch.bfloat16).contiguous().view(B * T, D)
-        keep = self._ctx.view(B * T, self.kv_total) if (self._ctx is not None and tuple(self._ctx.shape) == (B, T, self.kv_total)) else None
-        kv = ops.gemm(c, self.P["kv_all.w"], self.kv_total, out=keep)  # stable address across calls (captured graphs read it)
+        if out is None and self._ctx is not None and tuple(self._ctx.shape) == (B, T, self.kv_total):
+            out = self._ctx
+        kv = ops.gemm(c, self.P["kv_all.w"], self.kv_total, out=None if out is None else out.view(B * T, self.kv_total))
         self._ctx = kv.view(B, T, self.kv_total)
         return self._ctx
 
@@ -297,15 +339,30 @@ class UNet2DConditionModel:
         M, N = B * h * w, h * w
         b = p + ".transformer_blocks.0"
         hn = ops.groupnorm([x], *P[p + ".norm"], cfg.norm_num_groups, 1e-6, self.ws, silu=False)
-        t = ops.gemm(hn.view(M, C), P[p + ".proj_in.w"], C, bias=P[p + ".proj_in.b"])
-        qkv = ops.gemm(ops.layernorm(t, *P[b + ".ln1"]), P[b + ".qkv"], 3 * C).view(B, N, 3 * C)
-        a = ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads, (C // heads) ** -0.5)
-        t = ops.gemm(a.view(M, C), P[b + ".o1.w"], C, bias=P[b + ".o1.b"], residual=t)
-        q = ops.gemm(ops.layernorm(t, *P[b + ".ln2"]), P[b + ".q2"], C).view(B, N, C)
         off = self.kv_off[p]
-        a = ops.attention(q, self._ctx[..., off:off + C], self._ctx[..., off + C:off + 2 * C], heads, (C // heads) ** -0.5)
-        t = ops.gemm(a.view(M, C), P[b + ".o2.w"], C, bias=P[b + ".o2.b"], residual=t)
-        ff = ops.gemm(ops.layernorm(t, *P[b + ".ln3"]), P[b + ".ff1.w"], 8 * C, bias=P[b + ".ff1.b"], act=ops.ACT_GEGLU)
+        kc, vc = self._ctx[..., off:off + C], self._ctx[..., off + C:off + 2 * C]
+        scale = (C // heads) ** -0.5
+        if (b + ".qkv.cs") in P:
+            # LayerNorm folded: each producer GEMM emits the row statistics its consumer's epilogue needs (no LayerNorm launches)
+            stat = lambda: torch.empty((M, C // 32, 2), dtype=torch.float32, device=x.device)
+            s1, s2, s3 = stat(), stat(), stat()
+            t = ops.gemm(hn.view(M, C), P[p + ".proj_in.w"], C, bias=P[p + ".proj_in.b"], rowstat=s1)
+            qkv = ops.gemm(t, P[b + ".qkv"], 3 * C, bias=P[b + ".qkv.b"], ln=(s1, P[b + ".qkv.cs"], LN_EPS)).view(B, N, 3 * C)
+            a = ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads, scale)
+            t = ops.gemm(a.view(M, C), P[b + ".o1.w"], C, bias=P[b + ".o1.b"], residual=t, rowstat=s2)
+            q = ops.gemm(t, P[b + ".q2"], C, bias=P[b + ".q2.b"], ln=(s2, P[b + ".q2.cs"], LN_EPS)).view(B, N, C)
+            a = ops.attention(q, kc, vc, heads, scale)
+            t = ops.gemm(a.view(M, C), P[b + ".o2.w"], C, bias=P[b + ".o2.b"], residual=t, rowstat=s3)
+            ff = ops.gemm(t, P[b + ".ff1.w"], 8 * C, bias=P[b + ".ff1.b"], act=ops.ACT_GEGLU, ln=(s3, P[b + ".ff1.cs"], LN_EPS))
+        else:
+            t = ops.gemm(hn.view(M, C), P[p + ".proj_in.w"], C, bias=P[p + ".proj_in.b"])
+            qkv = ops.gemm(ops.layernorm(t, *P[b + ".ln1"]), P[b + ".qkv"], 3 * C).view(B, N, 3 * C)
+            a = ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads, scale)
+            t = ops.gemm(a.view(M, C), P[b + ".o1.w"], C, bias=P[b + ".o1.b"], residual=t)
+            q = ops.gemm(ops.layernorm(t, *P[b + ".ln2"]), P[b + ".q2"], C).view(B, N, C)
+            a = ops.attention(q, kc, vc, heads, scale)
+            t = ops.gemm(a.view(M, C), P[b + ".o2.w"], C, bias=P[b + ".o2.b"], residual=t)
+            ff = ops.gemm(ops.layernorm(t, *P[b + ".ln3"]), P[b + ".ff1.w"], 8 * C, bias=P[b + ".ff1.b"], act=ops.ACT_GEGLU)
         t = ops.gemm(ff, P[b + ".ff2.w"], C, bias=P[b + ".ff2.b"], residual=t)
         return ops.gemm(t, P[p + ".proj_out.w"], C, bias=P[p + ".proj_out.b"], residual=x.view(M, C)).view(B, h, w, C)
 
@@ -341,7 +398,8 @@ class UNet2DConditionModel:
                     x = self._transformer(f"up_blocks.{i}.attentions.{l}", x, rheads[i])
             if i < len(ch) - 1:
                 p = f"up_blocks.{i}.upsamplers.0.conv"
-                x = ops.conv2d([ops.upsample2x(x)], P[p + ".w"], out, bias=P[p + ".b"])
+                x = (ops.conv2d([x], P[p + ".w"], out, bias=P[p + ".b"], up2x=True) if self.fuse_up
+                     else ops.conv2d([ops.upsample2x(x)], P[p + ".w"], out, bias=P[p + ".b"]))
         hn = ops.groupnorm([x], *P["conv_norm_out"], cfg.norm_num_groups, cfg.norm_eps, self.ws, silu=True)
         B, h, w, _ = hn.shape
         eps = torch.empty((B, h, w, 4), dtype=torch.float32, device=self.device)

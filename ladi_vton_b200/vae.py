@@ -8,11 +8,13 @@ conv's epilogue as a per-pixel (1-mask) row scale).  State-dict key names follow
 NHWC bf16 internally; NCHW fp32 at the boundary.  quant_conv (1x1) is folded algebraically into encoder.conv_out at load
 time (both linear, no padding interaction); post_quant_conv stays separate because its bias meets conv_in's zero padding.
 """
+import os
+
 import torch
 
 from . import ops
 from .unet import _Cfg
-from .weights import f32, pack_conv, pack_linear
+from .weights import f32, pack_conv, pack_conv_up2x, pack_linear
 
 SD2_VAE = dict(in_channels=3, out_channels=3, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
                latent_channels=4, norm_num_groups=32, scaling_factor=0.18215, sample_size=512)
@@ -97,6 +99,7 @@ class AutoencoderKL:
         self.dtype = torch.bfloat16
         self.device = torch.device("cpu")
         self._sd, self.P = None, None
+        self.pack_gen = 0
 
     def eval(self):
         return self
@@ -123,9 +126,13 @@ class AutoencoderKL:
             device = torch.device(device)
             if device.type != "cuda":
                 raise RuntimeError("ladi_vton_b200 VAE runs on CUDA (sm_100a) only; there is no CPU path")
+            if self.P is not None and device == self.device:
+                return self  # already packed here (captured graphs hold these addresses)
             self.device = device
             if self._sd is not None:
                 self._pack()
+            elif self.P is not None:
+                raise RuntimeError("the state dict was released after packing; call load_state_dict again to move the VAE")
         return self
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -134,6 +141,7 @@ class AutoencoderKL:
         g = lambda k: sd[k].to(dev, torch.float32)
         P = {}
         ch, L, cz = cfg.block_out_channels, cfg.layers_per_block, cfg.latent_channels
+        self.fuse_up = os.environ.get("LADI_UP2X", "1") != "0"
 
         def conv(p, ci):
             P[p + ".w"], P[p + ".b"] = pack_conv(g(p + ".weight"), [ci]), f32(g(p + ".bias"))
@@ -154,9 +162,8 @@ class AutoencoderKL:
             resnet(p + ".resnets.0", c, c); resnet(p + ".resnets.1", c, c)
             a = p + ".attentions.0"
             norm(a + ".group_norm")
-            P[a + ".qk.w"] = pack_linear(torch.cat([g(a + ".query.weight"), g(a + ".key.weight")]))
-            P[a + ".qk.b"] = f32(torch.cat([g(a + ".query.bias"), g(a + ".key.bias")]))
-            P[a + ".v.w"], P[a + ".v.b"] = pack_linear(g(a + ".value.weight")), f32(g(a + ".value.bias"))
+            P[a + ".qkv.w"] = pack_linear(torch.cat([g(a + ".query.weight"), g(a + ".key.weight"), g(a + ".value.weight")]))
+            P[a + ".qkv.b"] = f32(torch.cat([g(a + ".query.bias"), g(a + ".key.bias"), g(a + ".value.bias")]))
             P[a + ".o.w"], P[a + ".o.b"] = pack_linear(g(a + ".proj_attn.weight")), f32(g(a + ".proj_attn.bias"))
 
         conv("encoder.conv_in", cfg.in_channels)
@@ -182,10 +189,17 @@ class AutoencoderKL:
             for l in range(L + 1):
                 resnet(f"decoder.up_blocks.{i}.resnets.{l}", prev if l == 0 else out, out)
             if i < len(ch) - 1:
-                conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", out)
+                p = f"decoder.up_blocks.{i}.upsamplers.0.conv"
+                if self.fuse_up:
+                    P[p + ".w"], P[p + ".b"] = pack_conv_up2x(g(p + ".weight"), [out]), f32(g(p + ".bias"))
+                else:
+                    conv(p, out)
         norm("decoder.conv_norm_out"); conv("decoder.conv_out", ch[0])
         self.P = P
         self.ws = ops.GroupNormWS(dev)
+        self.pack_gen += 1
+        if any(v.is_cuda for v in sd.values()):
+            self._sd = None
 
     # ------------------------------------------------------------------------------------------------------------------
     def _resnet(self, p, x, co):
@@ -198,22 +212,18 @@ class AutoencoderKL:
         return ops.conv2d([hn2], P[p + ".w2"], co, bias=P[p + ".b2"], residual=x)
 
     def _attn(self, a, x):
-        """Single-head d=C spatial attention (Appendix A.5): S = Q K^T (fp32 out), row softmax, O = P V, all on the GEMM kernel;
-        V^T is produced directly by swapping the GEMM operands (weights as the M side, tokens as the N side)."""
+        """Single-head d=C spatial attention (diffusers 0.14 AttentionBlock, Appendix A.5; src/models/vae.py:81-90,142-150): GroupNorm ->
+        one fused Q|K|V GEMM -> the flash kernel for a 512-wide head over the whole batch in ONE launch (the N x N score matrix is never
+        written; the reference's baddbmm + softmax + bmm materialises it per sample) -> proj_attn GEMM with the residual in its epilogue."""
         P = self.P
         B, h, w, C = x.shape
         N = h * w
-        assert N % 64 == 0, "VAE attention needs h*w to be a multiple of 64"
+        if C not in (256, 512):
+            raise NotImplementedError(f"VAE mid-block attention is built for C = 512 (256 for reduced-width test models), got {C}")
         hn = ops.groupnorm([x], *P[a + ".group_norm"], self.config.norm_num_groups, 1e-6, self.ws, silu=False)
-        hn2 = hn.view(B * N, C)
-        qk = ops.gemm(hn2, P[a + ".qk.w"], 2 * C, bias=P[a + ".qk.b"])
-        o = torch.empty((B * N, C), dtype=torch.bfloat16, device=x.device)
-        for b in range(B):
-            rows = slice(b * N, (b + 1) * N)
-            vt = ops.gemm(P[a + ".v.w"][:, :C], hn2[rows], N, bias=P[a + ".v.b"], bias_per_row=True)       # [C, N] = V^T
-            s = ops.gemm(qk[rows, :C], qk[rows, C:], N, out_fp32=True)                                    # [N, N]
-            ops.gemm(ops.softmax_rows(s, C ** -0.5), vt, C, out=o[rows])
-        return ops.gemm(o, P[a + ".o.w"], C, bias=P[a + ".o.b"], residual=x.view(B * N, C)).view(B, h, w, C)
+        qkv = ops.gemm(hn.view(B * N, C), P[a + ".qkv.w"], 3 * C, bias=P[a + ".qkv.b"]).view(B, N, 3 * C)
+        o = ops.attention_d512(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], C ** -0.5)
+        return ops.gemm(o.view(B * N, C), P[a + ".o.w"], C, bias=P[a + ".o.b"], residual=x.view(B * N, C)).view(B, h, w, C)
 
     def _mid(self, p, x):
         c = x.shape[3]
@@ -275,15 +285,17 @@ class AutoencoderKL:
                 x = self._resnet(f"decoder.up_blocks.{i}.resnets.{l}", x, c)
             if i < len(ch) - 1:
                 p = f"decoder.up_blocks.{i}.upsamplers.0.conv"
-                x = ops.conv2d([ops.upsample2x(x)], P[p + ".w"], c, bias=P[p + ".b"])
+                x = (ops.conv2d([x], P[p + ".w"], c, bias=P[p + ".b"], up2x=True) if self.fuse_up
+                     else ops.conv2d([ops.upsample2x(x)], P[p + ".w"], c, bias=P[p + ".b"]))
         last = None
         if rf is not None and int_layers and 1 in int_layers:  # vae.py:204-205, added AFTER norm + SiLU
             last = rf[len(int_layers) - 1 - int_layers.index(1)]
         hn = ops.groupnorm([x], *P["decoder.conv_norm_out"], cfg.norm_num_groups, 1e-6, self.ws, silu=True, add=last)
         img = torch.empty((B, x.shape[1], x.shape[2], 4), dtype=torch.float32, device=self.device)
-        ops.conv2d([hn], P["decoder.conv_out.w"], cfg.out_channels, bias=P["decoder.conv_out.b"], out=img, out_fp32=True)
-        if rf is not None and int_layers and 0 in int_layers:
-            raise NotImplementedError("int_layers containing 0 (image-space skip) is never used by the reference CLI")
+        res0 = None
+        if rf is not None and int_layers and 0 in int_layers:  # vae.py:209-210: image-space skip added AFTER conv_out (residual epilogue)
+            res0 = rf[len(int_layers) - 1 - int_layers.index(0)][..., :cfg.out_channels]
+        ops.conv2d([hn], P["decoder.conv_out.w"], cfg.out_channels, bias=P["decoder.conv_out.b"], out=img, out_fp32=True, residual=res0)
         return img
 
     def decode(self, z, intermediate_features=None, int_layers=None, return_dict=True):
@@ -301,6 +313,7 @@ class EMASC:
         self.in_channels, self.out_channels = list(in_channels), list(out_channels)
         self.device = torch.device("cpu")
         self._sd, self.P = None, None
+        self.pack_gen = 0
 
     def eval(self):
         return self
@@ -324,6 +337,8 @@ class EMASC:
             device = torch.device(device)
             if device.type != "cuda":
                 raise RuntimeError("ladi_vton_b200 EMASC runs on CUDA (sm_100a) only; there is no CPU path")
+            if self.P is not None and device == self.device:
+                return self
             self.device = device
             if self._sd is not None:
                 self._pack()
@@ -335,6 +350,7 @@ class EMASC:
         for i, (ci, co) in enumerate(zip(self.in_channels, self.out_channels)):
             self.P.append((pack_conv(g(f"conv.{i}.0.weight"), [ci]), f32(g(f"conv.{i}.0.bias")),
                            pack_conv(g(f"conv.{i}.2.weight"), [ci]), f32(g(f"conv.{i}.2.bias"))))
+        self.pack_gen += 1
 
     def __call__(self, feats, inv_masks=None):
         """feats: list of NHWC bf16 tensors; inv_masks: optional list of fp32 (1-mask) rows per scale => mask_features fused."""

@@ -56,3 +56,41 @@ def interleave_geglu(w, b):
 
 def f32(t):
     return t.detach().to(torch.float32).contiguous()
+
+
+def merge_up2x(w):
+    """Sub-pixel decomposition of `conv3x3(nearest_upsample_2x(x))` (diffusers Upsample2D): output pixel (2i+py, 2j+px) reads the 2x2
+    input pixels (i+py-1 .. i+py, j+px-1 .. j+px); the 3x3 taps that land on the same input pixel are summed (fp32).
+    w [co, ci, 3, 3] -> [4 (parity py*2+px), co, ci, 2, 2]."""
+    rows = {0: ([0], [1, 2]), 1: ([0, 1], [2])}  # parity -> kernel rows feeding tap 0 / tap 1
+    out = w.new_zeros((4,) + tuple(w.shape[:2]) + (2, 2))
+    for py in (0, 1):
+        for px in (0, 1):
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    acc = 0
+                    for ky in rows[py][ty]:
+                        for kx in rows[px][tx]:
+                            acc = acc + w[:, :, ky, kx]
+                    out[py * 2 + px, :, :, ty, tx] = acc
+    return out
+
+
+def pack_conv_up2x(w, src_channels):
+    """-> bf16 [4 * c_out, 4 taps * sum(pad64(c))]: the four parities' merged 2x2 weights stacked along the rows (the layout
+    ladi_conv2d_bf16 reads with up2x = 1)."""
+    m = merge_up2x(w.float())
+    return torch.cat([pack_conv(m[p], src_channels) for p in range(4)], dim=0).contiguous()
+
+
+def fold_layernorm(w, gamma, beta, bias=None):
+    """LayerNorm folded into the linear that consumes it:  LN(x) W^T + b = rstd * (x W'^T - mean * colsum(W')) + (W beta + b)  with
+    W' = W diag(gamma).  Returns (packed bf16 W', colsum fp32 [n_out] of the bf16-ROUNDED W' -- what the tensor core multiplies --,
+    bias' fp32 [n_out])."""
+    w, gamma, beta = w.float(), gamma.float(), beta.float()
+    wp = pack_linear(w * gamma[None, :])
+    colsum = wp.float().sum(dim=1).contiguous()
+    b = w @ beta
+    if bias is not None:
+        b = b + bias.float()
+    return wp, colsum, b.contiguous()

@@ -56,6 +56,17 @@ def prepare_mask_and_masked_image(image, mask):
     return mask, image * (mask < 0.5)
 
 
+def randn_tensor(shape, generator=None, dtype=None):
+    """diffusers.utils.randn_tensor (recalled, Appendix A.8), CPU: a LIST of generators draws each sample's (1, ...) slice from
+    its own generator; a one-element list is unwrapped."""
+    if isinstance(generator, (list, tuple)):
+        if len(generator) == 1:
+            generator = generator[0]
+        else:
+            return torch.cat([torch.randn((1,) + tuple(shape[1:]), generator=g, dtype=dtype) for g in generator], dim=0)
+    return torch.randn(tuple(shape), generator=generator, dtype=dtype)
+
+
 class _Step:
     def __init__(self, prev_sample, pred_original_sample):
         self.prev_sample = prev_sample
@@ -103,9 +114,15 @@ class DDIMScheduler:
         x0 = (sample - (1 - a_t) ** 0.5 * model_output) / a_t ** 0.5
         if self.config.clip_sample:
             x0 = x0.clamp(-1, 1)
-        assert eta == 0.0, "oracle restates the eta=0 path only (CLI never sets eta)"
-        direction = (1 - a_p) ** 0.5 * model_output
-        return _Step(a_p ** 0.5 * x0 + direction, x0)
+        # diffusers 0.14 DDIMScheduler._get_variance / step (recalled): sigma_t = eta * sqrt((1-a_prev)/(1-a_t) * (1 - a_t/a_prev));
+        # the CLI never sets eta, so sigma_t = 0 on the benchmarked path
+        variance = (1 - a_p) / (1 - a_t) * (1 - a_t / a_p)
+        std = eta * variance ** 0.5
+        direction = (1 - a_p - std ** 2) ** 0.5 * model_output
+        prev = a_p ** 0.5 * x0 + direction
+        if eta > 0:
+            prev = prev + std * randn_tensor(model_output.shape, generator=generator, dtype=model_output.dtype)
+        return _Step(prev, x0)
 
 
 class ClipEncoderLayer(nn.Module):

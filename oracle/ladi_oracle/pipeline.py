@@ -14,7 +14,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from .parts import mask_features, prepare_mask_and_masked_image
+from .parts import mask_features, prepare_mask_and_masked_image, randn_tensor
 
 
 class OracleTryOnPipeline:
@@ -24,6 +24,11 @@ class OracleTryOnPipeline:
         self.vae_scale_factor = 2 ** (len(vae.config.block_out_channels) - 1)  # tryon_pipe.py:138
         self.trace = None  # optional dict collecting intermediates for block-level parity tests
 
+    @staticmethod
+    def _sample(dist, generator):
+        """DiagonalGaussianDistribution.sample (src/models/vae.py:341-347) = mean + std * randn_tensor(mean.shape, generator)."""
+        return dist.mean + dist.std * randn_tensor(dist.mean.shape, generator=generator, dtype=dist.parameters.dtype)
+
     def _rec(self, k, v):
         if self.trace is not None:
             self.trace[k] = v.detach().clone() if torch.is_tensor(v) else v
@@ -31,7 +36,7 @@ class OracleTryOnPipeline:
     @torch.no_grad()
     def __call__(self, image, mask_image, pose_map, warped_cloth, prompt_embeds, negative_prompt_embeds=None,
                  height=None, width=None, num_inference_steps=50, guidance_scale=7.5, generator=None, latents=None,
-                 output_type="np", cloth_cond_rate=1.0, no_pose=False, cloth_input_type="warped"):
+                 output_type="np", cloth_cond_rate=1.0, no_pose=False, cloth_input_type="warped", eta=0.0):
         height = height or self.unet.config.sample_size * self.vae_scale_factor  # :584-585
         width = width or self.unet.config.sample_size * self.vae_scale_factor
         if height % 8 or width % 8:  # :372-373
@@ -49,7 +54,7 @@ class OracleTryOnPipeline:
         sf = self.vae.config.scaling_factor
         cloth = None
         if cloth_input_type == "warped":  # :639-647, RNG draw #1
-            cloth = sf * self.vae.encode(warped_cloth)[0].latent_dist.sample(generator=generator)
+            cloth = sf * self._sample(self.vae.encode(warped_cloth)[0].latent_dist, generator)
         elif cloth_input_type != "none":
             raise ValueError(f"Invalid cloth_input_type {cloth_input_type}")
         self.scheduler.set_timesteps(num_inference_steps)  # :650
@@ -57,12 +62,12 @@ class OracleTryOnPipeline:
         cloth_steps = (1 - cloth_cond_rate) * num_inference_steps  # :654
         h, w = height // self.vae_scale_factor, width // self.vae_scale_factor
         if latents is None:  # :410-425, RNG draw #2
-            latents = torch.randn((B, self.vae.config.latent_channels, h, w), generator=generator, dtype=ctx.dtype)
+            latents = randn_tensor((B, self.vae.config.latent_channels, h, w), generator=generator, dtype=ctx.dtype)
         latents = latents * self.scheduler.init_noise_sigma
         # prepare_mask_latents :427-492, RNG draw #3
         mask_l = F.interpolate(mask, size=(h, w)).to(ctx.dtype)
         post, feats = self.vae.encode(masked_image.to(ctx.dtype))
-        masked_l = sf * post.latent_dist.sample(generator=generator)
+        masked_l = sf * self._sample(post.latent_dist, generator)  # :445-450 samples per image with generator[i]: the same draws
         self._rec("cloth_latents", cloth)
         self._rec("masked_latents", masked_l)
         inter = None
@@ -91,7 +96,7 @@ class OracleTryOnPipeline:
             if cfg:
                 e_u, e_t = eps.chunk(2)
                 eps = e_u + guidance_scale * (e_t - e_u)
-            latents = self.scheduler.step(eps, t, latents, eta=0.0).prev_sample.to(self.vae.dtype)
+            latents = self.scheduler.step(eps, t, latents, eta=eta, generator=generator).prev_sample.to(self.vae.dtype)  # :337-345,740
         self._rec("final_latents", latents)
         z = 1 / sf * latents  # :349-359
         img = (self.vae.decode(z, inter, self.emasc_int_layers).sample if inter

@@ -318,7 +318,8 @@ def test_pointwise_glue(cuda):
 
 
 @pytest.mark.parametrize("cfg", [False, True])
-def test_ddim_cfg_step(cuda, cfg):
+@pytest.mark.parametrize("eta", [False, True])
+def test_ddim_cfg_step(cuda, cfg, eta):
     from ladi_vton_b200 import ops
     B, h, w, g = 2, 8, 6, 7.5
     Bp = 2 * B if cfg else B
@@ -327,19 +328,138 @@ def test_ddim_cfg_step(cuda, cfg):
     lat = rnd((B, 4, h, w), cuda, 2)
     lat0 = lat.clone()
     uin = torch.zeros((Bp, h, w, 32), dtype=torch.bfloat16, device=cuda)
-    coef = torch.tensor([[1.1, 0.3, 0.9, 0.2], [1.2, 0.4, 0.8, 0.1]], device=cuda)
+    coef = torch.tensor([[1.1, 0.3, 0.9, 0.2, 0.7, 0, 0, 0], [1.2, 0.4, 0.8, 0.1, 0.5, 0, 0, 0]], device=cuda)
     step = torch.tensor([1, 0], dtype=torch.int32, device=cuda)
-    ops.ddim_cfg_step(eps, lat, uin, cfg, g, coef, step)
+    noise = rnd((B, 4, h, w), cuda, 3) if eta else None
+    ops.ddim_cfg_step(eps, lat, uin, cfg, g, coef, step, noise=noise)
     e = eps.permute(0, 3, 1, 2)
     if cfg:
         e = e[:B] + g * (e[B:] - e[:B])
     ref = 0.8 * ((lat0 - 0.4 * e) * 1.2) + 0.1 * e
+    if eta:
+        ref = ref + 0.5 * noise  # DDIMScheduler.step: prev_sample += sigma_t * variance_noise
     torch.cuda.synchronize()
     assert torch.allclose(lat, ref, rtol=1e-5, atol=1e-5)
     assert step.tolist() == [2, 0]
-    assert torch.equal(uin[:B, ..., :4], ref.bfloat16().permute(0, 2, 3, 1))
+    assert torch.equal(uin[:B, ..., :4], lat.bfloat16().permute(0, 2, 3, 1))
     if cfg:
         assert torch.equal(uin[B:, ..., :4], uin[:B, ..., :4])
+
+
+def test_check_binarise(cuda):
+    """prepare_mask_and_masked_image's range checks + in-place binarisation on the device (tryon_pipe.py:630), flags instead of syncs."""
+    from ladi_vton_b200 import ops
+    img = (torch.rand((2, 3, 40, 24), device=cuda) * 2 - 1).contiguous()
+    mask = torch.rand((2, 1, 40, 24), device=cuda).contiguous()
+    ref = (mask >= 0.5).float()
+    flags = torch.zeros(2, dtype=torch.int32, device=cuda)
+    ops.check_binarise_(img, mask, flags)
+    assert flags.tolist() == [0, 0] and torch.equal(mask, ref)
+    img[1, 2, 7, 3] = 1.5
+    ops.check_binarise_(img, mask, flags)
+    assert flags.tolist() == [1, 0]
+    mask[0, 0, 0, 0] = -0.25
+    flags.zero_()
+    ops.check_binarise_(img * 0, mask, flags)
+    assert flags.tolist() == [0, 1] and float(mask[0, 0, 0, 0]) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------ wide single-head attention (VAE mid block)
+@pytest.mark.parametrize("D,B,nq,nkv", [(512, 2, 128, 128), (512, 1, 3072, 3072), (512, 2, 200, 200), (512, 1, 384, 1000), (256, 2, 128, 128),
+                                        (256, 3, 640, 640), (512, 1, 12288, 12288)])
+def test_attention_d512(cuda, D, B, nq, nkv):
+    """One head of width 512 (src/models/vae.py:81-90: diffusers AttentionBlock, softmax(q k^T / sqrt(C)) v), flash-style, vs fp32 torch on
+    the same bf16 inputs; q/k/v are column slices of one fused [B, N, 3D] projection buffer like the VAE passes them."""
+    from ladi_vton_b200 import ops
+    if nq == nkv:
+        qkv = rnd((B, nq, 3 * D), cuda, 1).bfloat16()
+        q, k, v = qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:]
+    else:
+        q = rnd((B, nq, D), cuda, 1).bfloat16()
+        kv = rnd((B, nkv, 2 * D), cuda, 2).bfloat16()
+        k, v = kv[..., :D], kv[..., D:]
+    k = (k.float() * 2.0).bfloat16()  # scores of std ~2 after the 1/sqrt(D) scale: a softmax that is not flat
+    scale = D ** -0.5
+    y = ops.attention_d512(q, k, v, scale)
+    torch.cuda.synchronize()
+    ref = torch.empty((B, nq, D), dtype=torch.float32, device=cuda)
+    for b in range(B):
+        for i in range(0, nq, 2048):  # chunked fp32 reference (12288^2 scores would be 600 MB at once)
+            sl = slice(i, min(nq, i + 2048))
+            ref[b, sl] = torch.softmax((q[b, sl].float() @ k[b].float().t()) * scale, dim=-1) @ v[b].float()
+    assert y.shape == (B, nq, D)
+    assert nerr(y, ref) < TOL_BF16
+
+
+# ------------------------------------------------------------------------------------------------ fused nearest-2x upsample + conv3x3
+@pytest.mark.parametrize("n,h,w,ci,co,pair", [(2, 8, 6, 64, 64, None), (2, 8, 6, 96, 160, None), (16, 8, 6, 128, 256, None), (1, 16, 12, 320, 320, True),
+                                               (3, 4, 4, 64, 72, None), (2, 32, 24, 128, 128, None), (1, 64, 48, 256, 256, None)])
+def test_conv_up2x(cuda, n, h, w, ci, co, pair):
+    """Upsample2D (F.interpolate(scale_factor=2, nearest) + conv3x3) as one sub-pixel convolution over the half-resolution tensor."""
+    from ladi_vton_b200 import ops, weights
+    x = rnd((n, h, w, ci), cuda, 1).bfloat16()
+    wt = rnd((co, ci, 3, 3), cuda, 2, (9 * ci) ** -0.5)
+    b = rnd((co,), cuda, 3)
+    y = ops.conv2d([x], weights.pack_conv_up2x(wt, [ci]), co, bias=b, up2x=True, pair=pair)
+    torch.cuda.synchronize()
+    assert y.shape == (n, 2 * h, 2 * w, co)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(up, wt.bfloat16().float(), b, padding=1).permute(0, 2, 3, 1)
+    assert nerr(y, ref) < TOL_BF16
+    # and equal (up to the rounding of the merged weights) to the materialised form on the same kernels
+    y2 = ops.conv2d([ops.upsample2x(x)], weights.pack_conv(wt, [ci]), co, bias=b)
+    assert nerr(y, y2) < TOL_BF16
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm folded into the GEMMs around it
+@pytest.mark.parametrize("M,C,N,bn", [(300, 320, 320, 0), (3072, 320, 960, 0), (768, 1280, 1280, 0), (200, 64, 192, 0), (512, 640, 640, 160), (512, 640, 640, 256)])
+def test_gemm_rowstat_and_ln_fold(cuda, M, C, N, bn):
+    """Producer: out = a W1^T + b1 + residual, plus per-(row, 32-column chunk) {sum, sum of squares} of what it stores.
+    Consumer: LayerNorm(out) W2^T + b2 computed from the RAW `out` with W2 diag(gamma) and the rank-1 epilogue correction."""
+    from ladi_vton_b200 import ops, weights
+    a = rnd((M, C), cuda, 1).bfloat16()
+    w1 = rnd((C, C), cuda, 2, C ** -0.5)
+    b1 = rnd((C,), cuda, 3)
+    res = (rnd((M, C), cuda, 4) * 2 + 0.7).bfloat16()  # non-zero row means: the correction term matters
+    stats = torch.empty((M, C // 32, 2), dtype=torch.float32, device=cuda)
+    t = ops.gemm(a, weights.pack_linear(w1), C, bias=b1, residual=res, rowstat=stats, force_bn=bn)
+    torch.cuda.synchronize()
+    tref = a.float() @ w1.bfloat16().float().t() + b1 + res.float()
+    assert nerr(t, tref) < TOL_BF16
+    ch = tref.view(M, C // 32, 32)
+    assert torch.allclose(stats[..., 0], ch.sum(-1), rtol=2e-3, atol=2e-2)
+    assert torch.allclose(stats[..., 1], (ch * ch).sum(-1), rtol=2e-3, atol=2e-2)
+    gamma, beta = torch.rand(C, device=cuda) + 0.5, rnd((C,), cuda, 5)
+    w2 = rnd((N, C), cuda, 6, C ** -0.5)
+    b2 = rnd((N,), cuda, 7)
+    wp, cs, bp = weights.fold_layernorm(w2, gamma, beta, b2)
+    y = ops.gemm(t, wp, N, bias=bp, ln=(stats, cs, 1e-5), force_bn=bn)
+    torch.cuda.synchronize()
+    ref = F.layer_norm(t.float(), (C,), gamma, beta, 1e-5) @ w2.float().t() + b2
+    assert nerr(y, ref) < 1.5 * TOL_BF16
+    # ... and it agrees with the stand-alone LayerNorm kernel followed by the plain GEMM
+    y2 = ops.gemm(ops.layernorm(t, gamma, beta), weights.pack_linear(w2), N, bias=b2, force_bn=bn)
+    assert nerr(y, y2) < 1.5 * TOL_BF16
+
+
+def test_gemm_ln_fold_geglu(cuda):
+    from ladi_vton_b200 import ops, weights
+    M, C = 384, 320
+    a = rnd((M, C), cuda, 1).bfloat16()
+    w1 = rnd((C, C), cuda, 2, C ** -0.5)
+    stats = torch.empty((M, C // 32, 2), dtype=torch.float32, device=cuda)
+    t = ops.gemm(a, weights.pack_linear(w1), C, rowstat=stats)
+    gamma, beta = torch.rand(C, device=cuda) + 0.5, rnd((C,), cuda, 5)
+    w2 = rnd((8 * C, C), cuda, 6, C ** -0.5)
+    b2 = rnd((8 * C,), cuda, 7)
+    wi, bi = weights.interleave_geglu(w2, b2)
+    wp, cs, bp = weights.fold_layernorm(wi, gamma, beta, bi)
+    y = ops.gemm(t, wp, 8 * C, bias=bp, act=ops.ACT_GEGLU, ln=(stats, cs, 1e-5))
+    torch.cuda.synchronize()
+    h = F.layer_norm(t.float(), (C,), gamma, beta, 1e-5) @ w2.float().t() + b2
+    v, g = h.chunk(2, dim=-1)
+    assert y.shape == (M, 4 * C)
+    assert nerr(y, v * F.gelu(g)) < 1.5 * TOL_BF16
 
 
 # ------------------------------------------------------------------------------------------------ CTA pairs (tcgen05 cta_group::2)

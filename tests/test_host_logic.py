@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     l = lib.load()  # raises if the .so is missing; getattr raises on a missing export
     for name in declared:
         assert hasattr(l, name)
-    assert l.ladi_abi_version() == 1
+    assert l.ladi_abi_version() == lib.ABI_VERSION == 2
     out = subprocess.run(["nm", "-D", "--defined-only", lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (ladi_\w+)", out))
     assert declared <= exported
@@ -119,10 +119,30 @@ def test_pipeline_host_validation_and_signature():
     with pytest.raises(ValueError, match="same shape"):
         pipe.check_inputs(None, 64, 64, 1, None, torch.zeros(1, 77, 8), torch.zeros(2, 77, 8))
     m = torch.tensor([[[[0.2, 0.7], [0.5, 0.49]]]])
-    mask, _ = pipe._prepare_mask_and_image(torch.zeros(1, 3, 2, 2), m)
+    mask, _ = pipe._prepare_mask_and_image(torch.zeros(1, 3, 2, 2), m, None)
     assert m.flatten().tolist() == [0.0, 1.0, 1.0, 0.0] and mask is m  # binarised IN PLACE like the reference
     with pytest.raises(ValueError, match="Image should be"):
-        pipe._prepare_mask_and_image(torch.full((1, 3, 2, 2), 2.0), torch.zeros(1, 1, 2, 2))
+        pipe._prepare_mask_and_image(torch.full((1, 3, 2, 2), 2.0), torch.zeros(1, 1, 2, 2), None)
+    with pytest.raises(ValueError, match="Mask should be"):
+        pipe._prepare_mask_and_image(torch.zeros(1, 3, 2, 2), torch.full((1, 1, 2, 2), 1.5), None)
+    # PIL / ndarray branch of prepare_mask_and_masked_image (no EMASC on this pipeline): uint8 RGB -> [-1, 1], L mask -> {0, 1}
+    import numpy as np
+    from PIL import Image
+    im = Image.fromarray(np.full((4, 2, 3), 255, dtype=np.uint8))
+    mk = Image.fromarray(np.array([[0, 255], [127, 128], [0, 0], [255, 255]], dtype=np.uint8))
+    mask, image = pipe._prepare_mask_and_image(im, mk, None)
+    assert image.shape == (1, 3, 4, 2) and float(image.min()) == 1.0 and mask.shape == (1, 1, 4, 2)
+    assert mask.flatten().tolist() == [0, 1, 0, 1, 0, 0, 1, 1]
+    with pytest.raises(TypeError, match="both"):
+        pipe._prepare_mask_and_image(torch.zeros(1, 3, 4, 2), mk, None)
+    # generator lists: one (1, ...) draw per sample from its own generator (randn_tensor's list branch)
+    from ladi_vton_b200.pipeline import _randn
+    gs = [torch.Generator().manual_seed(i) for i in (5, 6)]
+    got = _randn((2, 4, 3, 3), gs, torch.device("cpu"))
+    want = torch.cat([torch.randn((1, 4, 3, 3), generator=torch.Generator().manual_seed(i)) for i in (5, 6)])
+    assert torch.equal(got, want)
+    with pytest.raises(ValueError, match="list of generators"):
+        _randn((3, 4, 3, 3), [torch.Generator(), torch.Generator()], torch.device("cpu"))
     with pytest.raises(RuntimeError, match="CUDA"):
         pipe.to("cpu")
     with pytest.raises(RuntimeError, match="state_dict mismatch"):

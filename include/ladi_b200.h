@@ -248,6 +248,98 @@ LADI_API int ladi_upsample2x_bilinear_ac(const void* x, int n, int h, int w, int
 /* NHWC fp32 [n,h,w,pitch] (first c channels) -> NCHW fp32 clamped to [lo,hi] (inference.py:262 warped_cloth.clamp(-1,1)). */
 LADI_API int ladi_nhwc_f32_to_nchw_clamp(const float* x, int n, int c, int h, int w, int x_pitch, float lo, float hi, float* out, void* stream);
 
+/* ================================================================================================================================
+ * Module-level ABI: an opaque per-device engine handle + one entry point per module of the try-on path.
+ * What a non-Python host binds to run the reference's objects without re-writing their forward passes:
+ *   unet(x, t, encoder_hidden_states).sample           tryon_pipe.py:732 (diffusers UNet2DConditionModel.forward)   -> ladi_unet_forward
+ *   vae.encode(x) -> (posterior moments, 6 skips)      tryon_pipe.py:640,457; AutoencoderKL.py:145-157; vae.py:99-119 -> ladi_vae_encode
+ *   vae.decode(z, intermediate_features, int_layers)   tryon_pipe.py:352-353; AutoencoderKL.py:159-188; vae.py:183-212 -> ladi_vae_decode_emasc
+ *   emasc(features) + mask_features(features, mask)    tryon_pipe.py:684-685; emasc.py:37-40; data_utils.py:4-16     -> ladi_emasc_forward
+ *   inversion_adapter(clip_features)                   src/inference.py:276; inversion_adapter.py:22-28              -> ladi_inversion_adapter_forward
+ *   the denoising loop                                 tryon_pipe.py:713-747                                         -> ladi_denoise_loop
+ * Rules: all pointers are caller-owned device pointers; activations NHWC bf16 (channel pitch = multiple of 8); the caller supplies the
+ * activation workspace (ladi_workspace_bytes) and the stream; no call allocates, synchronises or uses an implicit stream, so every call is
+ * CUDA-graph capturable.  ladi_engine_create allocates the two scratch buffers all calls share (64 MB split-K partials, 16 MB GroupNorm
+ * statistics) and ladi_engine_destroy frees them.  One handle per (device, stream); calls on one handle are not concurrent. */
+typedef struct ladi_engine ladi_engine;
+
+/* one packed weight: name (the key the Python packer uses, e.g. "down_blocks.0.resnets.0.w1"), device pointer, rows x cols
+ * (bf16 matrices: cols = K = row pitch, layouts as documented at ladi_conv_desc; fp32 vectors: rows = 1) */
+typedef struct ladi_weight {
+  const char* name;
+  const void* ptr;
+  int rows, cols;
+} ladi_weight;
+
+typedef struct ladi_engine_config {
+  /* UNet2DConditionModel (SD-2-inpainting layout, hubconf.py:30-33) */
+  int unet_channels[4];        /* block_out_channels */
+  int unet_heads[4];           /* attention_head_dim = head COUNT per level in SD-2 configs (head width is always 64) */
+  int unet_down_attn[4];       /* down block i is a CrossAttnDownBlock2D */
+  int unet_up_attn[4];         /* up block i is a CrossAttnUpBlock2D */
+  int unet_layers_per_block;
+  int unet_in_channels, unet_out_channels;
+  float unet_norm_eps;
+  int norm_groups;             /* GroupNorm groups (32), UNet and VAE */
+  int fuse_upsample;           /* 1: upsampler weights are packed for the sub-pixel form (ladi_conv_desc.up2x) */
+  /* AutoencoderKL (LaDI-VTON fork, src/models/AutoencoderKL.py) */
+  int vae_channels[4];
+  int vae_layers_per_block, vae_latent_channels, vae_in_channels, vae_out_channels;
+  /* EMASC (hubconf.py:40-53) */
+  int emasc_scales;
+  int emasc_in[8], emasc_out[8], emasc_stride[8];   /* per scale: channels in / out, resolution divisor of the feature (1, 1, 2, 4, 8) */
+  /* InversionAdapter (hubconf.py:16-27) */
+  int adapter_dim, adapter_heads, adapter_mlp, adapter_hidden, adapter_out;
+  int plan_only;               /* 1: no device: the handle only answers ladi_workspace_bytes / ladi_engine_trace (tests, tooling) */
+} ladi_engine_config;
+
+LADI_API int ladi_engine_create(const ladi_engine_config* cfg, const ladi_weight* table, int n_weights, ladi_engine** out);
+LADI_API int ladi_engine_destroy(ladi_engine* engine);
+#define LADI_Q_TEMB_TOTAL 0 /* columns of the per-step bias table (sum of the resnets' widths) */
+#define LADI_Q_KV_TOTAL 1   /* columns of the text K/V buffer (sum over cross-attention layers of 2C) */
+#define LADI_Q_IN_PITCH 2   /* channel pitch of the UNet input buffer (in_channels rounded up to 8) */
+LADI_API int ladi_engine_query(const ladi_engine* engine, int what);
+
+#define LADI_MODULE_UNET 0        /* (batch = UNet batch, height = latent h, width = latent w) */
+#define LADI_MODULE_VAE_ENCODE 1  /* (batch, image height, image width) */
+#define LADI_MODULE_VAE_DECODE 2  /* (batch, latent h, latent w) */
+#define LADI_MODULE_EMASC 3       /* (batch, image height, image width) */
+#define LADI_MODULE_ADAPTER 4     /* (batch, height = tokens, width ignored) */
+/* bytes of caller workspace one call of `module` needs at this shape (a walk of the module body with the allocator only); -1 on error */
+LADI_API int64_t ladi_workspace_bytes(ladi_engine* engine, int module, int batch, int height, int width);
+/* the launch sequence of the last ladi_workspace_bytes walk, one op per line (tooling / the CPU test that pins it to the Python sequencing) */
+LADI_API const char* ladi_engine_trace(const ladi_engine* engine);
+
+/* eps = unet(x, t, ctx):  x_in NHWC bf16 [batch, h, w, in_pitch] (first in_channels valid; channel order latents4, mask1, masked4,
+ * pose18, cloth4, tryon_pipe.py:724-726); step_ptr device int32[2] = {row of `steps` to use, 0}; steps fp32 [n_steps][temb_total] =
+ * conv1.bias + time_emb_proj(silu(time_embedding(t_s))) per resnet (step-invariant, built once per call); ctx_kv bf16
+ * [batch, ctx_tokens, kv_total] = the text context already projected by every cross-attention layer's to_k / to_v;
+ * eps_out NHWC fp32 [batch, h, w, 4]. */
+LADI_API int ladi_unet_forward(ladi_engine* engine, const void* x_in, const int* step_ptr, const float* steps, const void* ctx_kv, int batch, int lat_h,
+                               int lat_w, int ctx_tokens, void* eps_out, void* workspace, int64_t workspace_bytes, void* stream);
+/* x NHWC bf16 [batch, H, W, 8] (3 valid channels) -> posterior moments NHWC fp32 [batch, H/8, W/8, 2*latent] (quant_conv folded in) and the
+ * retained encoder features (vae.py:100-109): skips[1] (= skips[2]) [batch,H,W,C0], skips[3] [batch,H/2,W/2,C0], skips[4] [.., /4, C1],
+ * skips[5] [.., /8, C2]; skips[0] is unused (the input itself); a null entry (or skips == NULL) keeps that feature in the workspace. */
+LADI_API int ladi_vae_encode(ladi_engine* engine, const void* x_nhwc8, int batch, int height, int width, float* moments, void* const* skips,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+/* z NHWC bf16 [batch, h, w, 8] (latents / scaling_factor, 4 valid channels) + the EMASC outputs feats[0..n_feats) in the reference's list
+ * order with their encoder layer indices int_layers[] (vae.py:183-212; n_feats = 0: plain decode) -> image NHWC fp32 [batch, 8h, 8w, 4]. */
+LADI_API int ladi_vae_decode_emasc(ladi_engine* engine, const void* z_nhwc8, int batch, int lat_h, int lat_w, const void* const* feats, int n_feats,
+                                   const int* int_layers, float* image_out, void* workspace, int64_t workspace_bytes, void* stream);
+/* per scale i: outs[i] = conv3x3(silu(conv3x3(feats[i]))) * inv_masks[i] (fp32 per output pixel = 1 - nearest-resized mask; NULL: no
+ * masking); feats / outs NHWC bf16 at resolution (height, width) / emasc_stride[i]. */
+LADI_API int ladi_emasc_forward(ladi_engine* engine, const void* const* feats, const float* const* inv_masks, int batch, int height, int width,
+                                void* const* outs, void* workspace, int64_t workspace_bytes, void* stream);
+/* feats bf16 [batch, tokens, adapter_dim] (CLIP ViT-H last_hidden_state) -> out bf16 [batch, adapter_out] */
+LADI_API int ladi_inversion_adapter_forward(ladi_engine* engine, const void* feats, int batch, int tokens, void* out, void* workspace,
+                                            int64_t workspace_bytes, void* stream);
+/* n_steps x (ladi_unet_forward + ladi_ddim_cfg_step) enqueued on `stream`: unet_in NHWC bf16 [cfg ? 2*batch : batch, h, w, in_pitch] with
+ * the static channels already written, latents NCHW fp32 [batch,4,h,w], step_ptr device int32[2] zeroed by the caller (advances on the
+ * device: no host sync in the loop), coef fp32 [n_steps][8] (see ladi_ddim_cfg_step), eps_scratch fp32 [cfg ? 2*batch : batch, h, w, 4]. */
+LADI_API int ladi_denoise_loop(ladi_engine* engine, void* unet_in, float* latents, int* step_ptr, const float* steps, const float* coef, const void* ctx_kv,
+                               int batch, int lat_h, int lat_w, int ctx_tokens, int cfg, float guidance, int n_steps, float* eps_scratch, void* workspace,
+                               int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,7 +9,7 @@ per call -- an HBM-bound chain of GEMMs on the tcgen05 kernel with GELU(erf) / r
 """
 import torch
 
-from . import ops
+from . import engine as eng, lib, ops
 from .weights import f32, pack_linear
 
 
@@ -80,6 +80,10 @@ class InversionAdapter:
                      ("l0", "layers.0"), ("l3", "layers.3"), ("l6", "layers.6")):
             P[n + ".w"], P[n + ".b"] = pack_linear(g(k + ".weight")), f32(g(k + ".bias"))
         self.P = P
+        self.engine = None
+        if eng.enabled() and self.device.type == "cuda":
+            self.engine = eng.Engine(eng.flatten(P, "adapter."), adapter_dim=self.dim, adapter_heads=self.heads, adapter_mlp=self.mlp_dim,
+                                     adapter_hidden=self.hidden, adapter_out=self.out_dim)
 
     def __call__(self, x):
         """x [B, 257, 1280] (CLIP vision last_hidden_state, any float dtype) -> [B, 16384] bf16."""
@@ -87,6 +91,11 @@ class InversionAdapter:
         B, T, _ = x.shape
         hd = d // self.heads
         xb = x.to(self.device, torch.bfloat16).contiguous()
+        if getattr(self, "engine", None) is not None and ops.PROFILE is None and lib.RECORD is None:  # one ABI call (csrc/engine.cu adapter_forward)
+            out = torch.empty((B, self.out_dim), dtype=torch.bfloat16, device=self.device)
+            ws = self.engine.workspace(eng.MODULE_ADAPTER, B, T, 0)
+            lib.call("ladi_inversion_adapter_forward", self.engine.h, ops._ptr(xb), B, T, ops._ptr(out), ops._ptr(ws), ws.numel(), ops._stream())
+            return out
         y = ops.layernorm(xb.view(B * T, d), *P["ln1"])                                  # pre-LN over all tokens
         kv = ops.gemm(y, P["kv.w"], 2 * d, bias=P["kv.b"]).view(B, T, 2 * d)
         y0 = y.view(B, T, d)[:, 0]                                                      # CLS rows, pitch T*d

@@ -895,9 +895,14 @@ attention_d512_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
       }
       l = l * alpha + ((s0 + s1) + (s2 + s3));
-      if (j > 0 && __any_sync(0xffffffffu, moved)) {   // rare: bring this thread's 128 accumulator columns to the new scale
+      // EVERY phase of o_ready is observed, in order (a parity wait only tells "the phase before the current one": skipping phases made
+      // the final wait below pass while only P(0) V(0) had completed whenever the V stream ran late).  P(j-1) V(j-1) runs right behind
+      // S(j) on the tensor pipe, so by now it is normally long done.
+      if (j > 0) {
         ptx::mbar_wait(o_ready, (j - 1) & 1);
         ptx::tc_fence_after();
+      }
+      if (j > 0 && __any_sync(0xffffffffu, moved)) {   // rare: bring this thread's 128 accumulator columns to the new scale
 #pragma unroll 1
         for (int c = 0; c < OCOLS; c += 32) {
           uint32_t o[32];

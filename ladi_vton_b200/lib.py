@@ -39,7 +39,25 @@ class AttnDesc(C.Structure):
     ]
 
 
+class Weight(C.Structure):  # ladi_weight
+    _fields_ = [("name", C.c_char_p), ("ptr", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int)]
+
+
+class EngineConfig(C.Structure):  # ladi_engine_config, field for field
+    _fields_ = [
+        ("unet_channels", C.c_int * 4), ("unet_heads", C.c_int * 4), ("unet_down_attn", C.c_int * 4), ("unet_up_attn", C.c_int * 4),
+        ("unet_layers_per_block", C.c_int), ("unet_in_channels", C.c_int), ("unet_out_channels", C.c_int), ("unet_norm_eps", C.c_float),
+        ("norm_groups", C.c_int), ("fuse_upsample", C.c_int),
+        ("vae_channels", C.c_int * 4), ("vae_layers_per_block", C.c_int), ("vae_latent_channels", C.c_int), ("vae_in_channels", C.c_int),
+        ("vae_out_channels", C.c_int),
+        ("emasc_scales", C.c_int), ("emasc_in", C.c_int * 8), ("emasc_out", C.c_int * 8), ("emasc_stride", C.c_int * 8),
+        ("adapter_dim", C.c_int), ("adapter_heads", C.c_int), ("adapter_mlp", C.c_int), ("adapter_hidden", C.c_int), ("adapter_out", C.c_int),
+        ("plan_only", C.c_int),
+    ]
+
+
 _P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64
+_PP = C.POINTER(C.c_void_p)
 SIGNATURES = {
     "ladi_abi_version": ([], C.c_int),
     "ladi_last_error": ([], C.c_char_p),
@@ -79,10 +97,23 @@ SIGNATURES = {
     "ladi_maxpool2_nhwc": ([_P, _I, _I, _I, _I, _P, _P], _I),
     "ladi_upsample2x_bilinear_ac": ([_P, _I, _I, _I, _I, _P, _P], _I),
     "ladi_nhwc_f32_to_nchw_clamp": ([_P, _I, _I, _I, _I, _I, _F, _F, _P, _P], _I),
+    # ---- module-level ABI (csrc/engine.cu)
+    "ladi_engine_create": ([C.POINTER(EngineConfig), C.POINTER(Weight), _I, _PP], _I),
+    "ladi_engine_destroy": ([_P], _I),
+    "ladi_engine_query": ([_P, _I], _I),
+    "ladi_workspace_bytes": ([_P, _I, _I, _I, _I], _L),
+    "ladi_engine_trace": ([_P], C.c_char_p),
+    "ladi_unet_forward": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _L, _P], _I),
+    "ladi_vae_encode": ([_P, _P, _I, _I, _I, _P, _PP, _P, _L, _P], _I),
+    "ladi_vae_decode_emasc": ([_P, _P, _I, _I, _I, _PP, _I, C.POINTER(C.c_int), _P, _P, _L, _P], _I),
+    "ladi_emasc_forward": ([_P, _PP, _PP, _I, _I, _I, _PP, _P, _L, _P], _I),
+    "ladi_inversion_adapter_forward": ([_P, _P, _I, _I, _P, _P, _L, _P], _I),
+    "ladi_denoise_loop": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _I, _P, _P, _L, _P], _I),
 }
 
 ABI_VERSION = 2
 _lib = None
+RECORD = None  # tests/test_engine_trace.py: a list -> call() appends (name, args) and launches nothing (CPU-side sequencing check)
 launches = 0  # number of kernel-launching ABI calls made by this process (bench.py reports it as gpu_launches)
 
 
@@ -107,6 +138,9 @@ def load():
 def call(name, *args):
     """Invoke an ABI entry point; non-zero return -> RuntimeError(ladi_last_error())."""
     global launches
+    if RECORD is not None:
+        RECORD.append((name, args))
+        return 0
     lib = load()
     rc = getattr(lib, name)(*args)
     if rc != 0:

@@ -27,6 +27,8 @@ def _call(name, flops, *args, tag=""):
 
 
 def _stream():
+    if lib.RECORD is not None:  # sequencing check on CPU tensors: nothing is launched
+        return C.c_void_p(0)
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -52,6 +54,8 @@ SPLITK_WS_BYTES = 64 << 20
 def splitk_workspace(device):
     """Persistent fp32 scratch for split-K partial sums (one per device; allocated before any graph capture)."""
     ws = _SPLITK_WS.get(device)
+    if ws is None and lib.RECORD is not None:
+        return torch.empty(1024, dtype=torch.float32)
     if ws is None:
         ws = _SPLITK_WS[device] = torch.empty(SPLITK_WS_BYTES // 4, dtype=torch.float32, device=device)
     return ws
@@ -200,6 +204,8 @@ class GroupNormWS:
 
     def get(self, n, hw, groups):
         need = n * lib.load().ladi_groupnorm_chunks(hw) * groups * 2
+        if lib.RECORD is not None:
+            return torch.empty(need, dtype=torch.float32)
         if self.buf is None or self.buf.numel() < need:
             if self.buf is not None:
                 self._retired.append(self.buf)  # an earlier, smaller session's captured graph still reads/writes this address

@@ -8,11 +8,12 @@ conv's epilogue as a per-pixel (1-mask) row scale).  State-dict key names follow
 NHWC bf16 internally; NCHW fp32 at the boundary.  quant_conv (1x1) is folded algebraically into encoder.conv_out at load
 time (both linear, no padding interaction); post_quant_conv stays separate because its bias meets conv_in's zero padding.
 """
+import ctypes as C
 import os
 
 import torch
 
-from . import ops
+from . import engine as eng, lib, ops
 from .unet import _Cfg
 from .weights import f32, pack_conv, pack_conv_up2x, pack_linear
 
@@ -200,6 +201,18 @@ class AutoencoderKL:
         self.pack_gen += 1
         if any(v.is_cuda for v in sd.values()):
             self._sd = None
+        self.engine = None
+        if eng.enabled() and dev.type == "cuda":
+            self.engine = eng.Engine(eng.flatten(P), **self.engine_config())
+
+    def engine_config(self):
+        cfg = self.config
+        return dict(vae_channels=cfg.block_out_channels, vae_layers_per_block=cfg.layers_per_block, vae_latent_channels=cfg.latent_channels,
+                    vae_in_channels=cfg.in_channels, vae_out_channels=cfg.out_channels, norm_groups=cfg.norm_num_groups,
+                    fuse_upsample=int(self.fuse_up), emasc_scales=5)
+
+    def _use_engine(self):
+        return getattr(self, "engine", None) is not None and ops.PROFILE is None and lib.RECORD is None
 
     # ------------------------------------------------------------------------------------------------------------------
     def _resnet(self, p, x, co):
@@ -244,6 +257,14 @@ class AutoencoderKL:
             B, _, H, W = x.shape
             xin = torch.zeros((B, H, W, 8), dtype=torch.bfloat16, device=self.device)
             ops.nchw_to_nhwc(x.to(self.device, torch.float32).contiguous(), xin)
+        if self._use_engine():  # one ABI call (csrc/engine.cu vae_encode); the retained features are written into caller buffers
+            mk = lambda c, f: torch.empty((B, H // f, W // f, c), dtype=torch.bfloat16, device=self.device)
+            f1, f3, f4, f5 = mk(ch[0], 1), mk(ch[0], 2), mk(ch[1], 4), mk(ch[2], 8)
+            mom = torch.empty((B, H // 8, W // 8, 2 * cfg.latent_channels), dtype=torch.float32, device=self.device)
+            ws = self.engine.workspace(eng.MODULE_VAE_ENCODE, B, H, W)
+            lib.call("ladi_vae_encode", self.engine.h, ops._ptr(xin), B, H, W, ops._ptr(mom), eng.ptr_array([None, f1, f1, f3, f4, f5]), ops._ptr(ws),
+                     ws.numel(), ops._stream())
+            return mom, [xin[..., :cin], f1, f1, f3, f4, f5]
         h = ops.conv2d([xin[..., :cin]], P["encoder.conv_in.w"], ch[0], bias=P["encoder.conv_in.b"])
         feats = [xin[..., :cin], h]
         for i, c in enumerate(ch):
@@ -273,6 +294,16 @@ class AutoencoderKL:
         B, _, h, w = z.shape
         zin = torch.zeros((B, h, w, 8), dtype=torch.bfloat16, device=self.device)
         ops.nchw_to_nhwc(z.to(self.device, torch.float32).contiguous(), zin, scale=scale)
+        if self._use_engine():  # one ABI call (csrc/engine.cu vae_decode)
+            img = torch.empty((B, 8 * h, 8 * w, 4), dtype=torch.float32, device=self.device)
+            fl = list(feats) if feats else []
+            for t in fl:
+                assert t.dtype == torch.bfloat16 and t.stride(3) == 1 and t.stride(2) == (t.shape[3] + 7) // 8 * 8, "EMASC features: dense NHWC bf16 (pitch = channels rounded up to 8)"
+            layers = (C.c_int * max(1, len(fl)))(*[int(i) for i in (int_layers or [])][:len(fl)])
+            ws = self.engine.workspace(eng.MODULE_VAE_DECODE, B, h, w)
+            lib.call("ladi_vae_decode_emasc", self.engine.h, ops._ptr(zin), B, h, w, eng.ptr_array(fl, max(1, len(fl))), len(fl), layers, ops._ptr(img),
+                     ops._ptr(ws), ws.numel(), ops._stream())
+            return img
         zq = torch.zeros((B, h, w, 8), dtype=torch.bfloat16, device=self.device)
         ops.gemm(zin.view(B * h * w, 8)[:, :cz], P["post_quant.w"], cz, bias=P["post_quant.b"], out=zq.view(B * h * w, 8))
         x = ops.conv2d([zq[..., :cz]], P["decoder.conv_in.w"], rch[0], bias=P["decoder.conv_in.b"])
@@ -351,9 +382,36 @@ class EMASC:
             self.P.append((pack_conv(g(f"conv.{i}.0.weight"), [ci]), f32(g(f"conv.{i}.0.bias")),
                            pack_conv(g(f"conv.{i}.2.weight"), [ci]), f32(g(f"conv.{i}.2.bias"))))
         self.pack_gen += 1
+        self.engine = None
+        if eng.enabled() and self.device.type == "cuda":
+            W = {}
+            for i, (w1, b1, w2, b2) in enumerate(self.P):
+                W.update({f"emasc.{i}.w1": w1, f"emasc.{i}.b1": b1, f"emasc.{i}.w2": w2, f"emasc.{i}.b2": b2})
+            self._engine_weights = W
+            self.engine = {}  # one handle per resolution pyramid (the strides are part of the handle's config), built on first use
+
+    def _engine_for(self, feats):
+        H, Wd = feats[0].shape[1], feats[0].shape[2]
+        strides = tuple(H // f.shape[1] for f in feats)
+        e = self.engine.get(strides)
+        if e is None:
+            e = self.engine[strides] = eng.Engine(self._engine_weights, emasc_scales=len(feats), emasc_in=self.in_channels, emasc_out=self.out_channels,
+                                                  emasc_stride=strides)
+        return e, H, Wd
 
     def __call__(self, feats, inv_masks=None):
         """feats: list of NHWC bf16 tensors; inv_masks: optional list of fp32 (1-mask) rows per scale => mask_features fused."""
+        if getattr(self, "engine", None) is not None and ops.PROFILE is None and lib.RECORD is None and len(feats) == len(self.P):
+            e, H, Wd = self._engine_for(feats)  # one ABI call (csrc/engine.cu emasc_forward)
+            B = feats[0].shape[0]
+            outs = []
+            for f, co in zip(feats, self.out_channels):
+                assert f.dtype == torch.bfloat16 and f.stride(3) == 1 and f.stride(2) == (f.shape[3] + 7) // 8 * 8 and H % f.shape[1] == 0
+                outs.append(torch.empty((B, f.shape[1], f.shape[2], (co + 7) // 8 * 8), dtype=torch.bfloat16, device=self.device)[..., :co])
+            ws = e.workspace(eng.MODULE_EMASC, B, H, Wd)
+            inv = eng.ptr_array(inv_masks) if inv_masks is not None else None
+            lib.call("ladi_emasc_forward", e.h, eng.ptr_array(feats), inv, B, H, Wd, eng.ptr_array(outs), ops._ptr(ws), ws.numel(), ops._stream())
+            return outs
         out = []
         for i, f in enumerate(feats):
             w1, b1, w2, b2 = self.P[i]

@@ -1,0 +1,208 @@
+"""CPU test (no GPU needed): the launch sequences of the module-level C ABI (csrc/engine.cu: ladi_unet_forward, ladi_vae_encode,
+ladi_vae_decode_emasc, ladi_emasc_forward, ladi_inversion_adapter_forward) are pinned, op by op and operand by operand, to the Python
+sequencing of the same kernels in ladi_vton_b200/{unet,vae,adapter}.py -- the sequencing every GPU parity test of round 1 validated
+against the oracle.  The C++ side is walked in plan mode (no launches; `ladi_engine_trace`), the Python side runs on CPU tensors with
+the ABI calls recorded instead of executed (`lib.RECORD`).  Addresses differ (workspace offsets vs torch allocations), so both traces
+are normalised to (buffer id, byte offset) by data flow: a buffer is born where an op writes it, reads resolve to the youngest buffer
+containing the address, external operands (weights, inputs) are numbered by first appearance."""
+import ctypes as C
+import re
+
+import pytest
+import torch
+
+
+def _fmt_conv(d):
+    g = lambda a, i: int(a[i] or 0)
+    return (f"conv k={d.ksize} s={d.stride} p={d.pad_lo} up={d.up2x} n={d.n} h={d.h_out} w={d.w_out} hin={d.h_in} win={d.w_in} cout={d.c_out} nsrc={d.n_src} "
+            f"src0=@{g(d.src, 0):x} c0={d.src_c[0]} p0={d.src_pitch[0]} src1=@{g(d.src, 1):x} c1={d.src_c[1]} p1={d.src_pitch[1]} nsc={d.n_sc} "
+            f"sc0=@{g(d.sc, 0):x} sc0c={d.sc_c[0]} sc0p={d.sc_pitch[0]} sc1=@{g(d.sc, 1):x} sc1c={d.sc_c[1]} sc1p={d.sc_pitch[1]} "
+            f"wt=@{int(d.weight or 0):x} K={d.k_total} wp={d.weight_pitch} bias=@{int(d.bias or 0):x} bpr={d.bias_per_row} bss={d.bias_step_stride} "
+            f"step=@{int(d.step_ptr or 0):x} res=@{int(d.residual or 0):x} rp={d.residual_pitch} rs=@{int(d.row_scale or 0):x} act={d.act} "
+            f"out=@{int(d.out or 0):x} op={d.out_pitch} f32={d.out_fp32}")
+
+
+def _v(x):
+    return int(getattr(x, "value", x) or 0)
+
+
+def python_trace(records):
+    lines = []
+    for name, a in records:
+        if name == "ladi_conv2d_bf16":
+            lines.append(_fmt_conv(a[0]._obj))
+        elif name == "ladi_groupnorm_stats":
+            lines.append(f"gn_stats x0=@{_v(a[0]):x} c0={a[1]} p0={a[2]} x1=@{_v(a[3]):x} c1={a[4]} p1={a[5]} n={a[6]} hw={a[7]} groups={a[8]}")
+        elif name == "ladi_groupnorm_apply":
+            lines.append(f"gn_apply x0=@{_v(a[0]):x} c0={a[1]} p0={a[2]} x1=@{_v(a[3]):x} c1={a[4]} p1={a[5]} n={a[6]} hw={a[7]} groups={a[8]} gamma=@{_v(a[10]):x} "
+                         f"beta=@{_v(a[11]):x} eps={a[12]:.3g} silu={a[13]} add=@{_v(a[14]):x} ap={a[15]} out=@{_v(a[16]):x} op={a[17]}")
+        elif name == "ladi_layernorm":
+            lines.append(f"ln x=@{_v(a[0]):x} xp={a[1]} rows={a[2]} c={a[3]} gamma=@{_v(a[4]):x} beta=@{_v(a[5]):x} eps={a[6]:.3g} out=@{_v(a[7]):x} op={a[8]}")
+        elif name in ("ladi_attention_bf16", "ladi_attention_d512_bf16"):
+            d = a[0]._obj
+            hd = 64 if name == "ladi_attention_bf16" else d.head_dim
+            lines.append(f"attn d={hd} batch={d.batch} heads={d.heads} nq={d.nq} nkv={d.nkv} q=@{int(d.q):x} qp={d.q_pitch} qbs={d.q_batch_stride} k=@{int(d.k):x} "
+                         f"kp={d.k_pitch} kbs={d.k_batch_stride} v=@{int(d.v):x} vp={d.v_pitch} vbs={d.v_batch_stride} out=@{int(d.out):x} op={d.out_pitch} "
+                         f"obs={d.out_batch_stride} scale={d.scale:.6g}")
+        elif name == "ladi_add_bf16":
+            lines.append(f"add a=@{_v(a[0]):x} b=@{_v(a[1]):x} out=@{_v(a[2]):x} count={a[3]}")
+        elif name == "ladi_upsample2x_nhwc":
+            lines.append(f"upsample2x x=@{_v(a[0]):x} n={a[1]} h={a[2]} w={a[3]} c={a[4]} out=@{_v(a[5]):x}")
+        elif name == "ladi_cls_attention":
+            lines.append(f"cls_attn q=@{_v(a[0]):x} qp={a[1]} kv=@{_v(a[2]):x} kvp={a[3]} batch={a[4]} tokens={a[5]} heads={a[6]} hd={a[7]} out=@{_v(a[9]):x} op={a[10]}")
+        else:
+            lines.append(f"{name} (layout / pointwise op outside the module bodies)")
+    return lines
+
+
+def _out_bytes(op, f):
+    """Bytes the op writes starting at its `out` address (for the data-flow normalisation)."""
+    i = lambda k: int(f[k])
+    if op == "conv":
+        return ((i("n") * i("h") * i("w") - 1) * i("op") + (i("cout") // (2 if i("act") == 2 else 1))) * (4 if i("f32") else 2)
+    if op == "gn_apply":
+        return ((i("n") * i("hw") - 1) * i("op") + i("c0") + i("c1")) * 2
+    if op == "ln":
+        return ((i("rows") - 1) * i("op") + i("c")) * 2
+    if op == "attn":
+        width = i("heads") * 64 if i("d") == 64 else i("d")
+        return ((i("batch") - 1) * i("obs") + (i("nq") - 1) * i("op") + width) * 2
+    if op == "add":
+        return i("count") * 2
+    if op == "upsample2x":
+        return i("n") * 4 * i("h") * i("w") * i("c") * 2
+    if op == "cls_attn":
+        return ((i("batch") - 1) * i("op") + i("heads") * i("hd")) * 2
+    return 0
+
+
+def normalise(lines):
+    """@address -> B<k>+off for buffers written inside the trace (youngest containing buffer), X<k> for external operands."""
+    live, ext, out, nbuf = [], {}, [], 0  # live: [(start, end, id)], youngest last
+    for ln in lines:
+        op = ln.split(" ", 1)[0]
+        f = dict(re.findall(r"(\w+)=(\S+)", ln))
+        w_addr = int(f["out"][1:], 16) if "out" in f else None
+
+        def resolve(a):
+            if a == 0:
+                return "NULL"
+            for s, e, k in reversed(live):
+                if s <= a < e:
+                    return f"B{k}+{a - s}"
+            if a not in ext:
+                ext[a] = len(ext)
+            return f"X{ext[a]}"
+        toks = []
+        for k, v in re.findall(r"(\w+)=(\S+)", ln):
+            if v.startswith("@"):
+                if k == "out":
+                    continue
+                toks.append(f"{k}={resolve(int(v[1:], 16))}")
+            else:
+                toks.append(f"{k}={v}")
+        if w_addr is not None:
+            size = _out_bytes(op, f)
+            # every write gives birth to a buffer (no op of the module bodies writes into a slice of a buffer born inside the trace); older
+            # buffers it overlaps are dead -- the C++ allocator re-uses freed workspace, torch never overlaps
+            live[:] = [(s, e, k) for s, e, k in live if e <= w_addr or s >= w_addr + size]
+            live.append((w_addr, w_addr + size, nbuf))
+            toks.append(f"out=B{nbuf}")
+            nbuf += 1
+        out.append(op + " " + " ".join(toks))
+    return out
+
+
+def compare(py_records, cpp_trace, what):
+    a = normalise(python_trace(py_records))
+    b = normalise([l for l in cpp_trace.splitlines() if l.strip()])
+    for i, (x, y) in enumerate(zip(a, b)):
+        assert x == y, f"{what}: op {i} differs\n  python: {x}\n  c++   : {y}"
+    assert len(a) == len(b), f"{what}: {len(a)} Python ops vs {len(b)} C++ ops"
+    return len(a)
+
+
+@pytest.fixture()
+def record():
+    from ladi_vton_b200 import lib
+    lib.RECORD = []
+    yield lib
+    lib.RECORD = None
+
+
+def _cpu_pack(model):
+    model.device = torch.device("cpu")
+    model._pack()
+    return model
+
+
+@pytest.mark.parametrize("B,h,w", [(2, 16, 8), (3, 8, 16)])
+@pytest.mark.parametrize("fuse", ["1", "0"])
+def test_unet_sequence_matches_python(record, monkeypatch, B, h, w, fuse):
+    from ladi_vton_b200 import UNet2DConditionModel, engine as eng, synthetic as S, unet_param_shapes
+    monkeypatch.setenv("LADI_UP2X", fuse)
+    unet = UNet2DConditionModel(**S.SMALL_UNET)
+    unet._sd = S.random_state_dict(unet_param_shapes(S.SMALL_UNET), 1)
+    _cpu_pack(unet)
+    e = eng.Engine(eng.flatten(unet.P), plan_only=True, **unet.engine_config())
+    assert e.query(eng.Q_TEMB_TOTAL) == unet.temb_total and e.query(eng.Q_KV_TOTAL) == unet.kv_total and e.query(eng.Q_IN_PITCH) == unet.in_pitch
+    unet._steps = torch.zeros((4, unet.temb_total))
+    unet._ctx = torch.zeros((B, 77, unet.kv_total), dtype=torch.bfloat16)
+    x = torch.zeros((B, h, w, unet.in_pitch), dtype=torch.bfloat16)
+    unet.forward_nhwc(x, torch.zeros(2, dtype=torch.int32))
+    n = compare(record.RECORD, e.trace(eng.MODULE_UNET, B, h, w), "UNet forward")
+    assert n > 300
+    assert e.workspace_bytes(eng.MODULE_UNET, B, h, w) > 0
+
+
+@pytest.mark.parametrize("fuse", ["1", "0"])
+def test_vae_emasc_sequences_match_python(record, monkeypatch, fuse):
+    from ladi_vton_b200 import AutoencoderKL, EMASC, engine as eng, synthetic as S
+    from ladi_vton_b200.vae import vae_param_shapes
+    monkeypatch.setenv("LADI_UP2X", fuse)
+    vae = AutoencoderKL(**S.SMALL_VAE)
+    vae._sd = S.random_state_dict(vae_param_shapes(S.SMALL_VAE), 2)
+    _cpu_pack(vae)
+    e = eng.Engine(eng.flatten(vae.P), plan_only=True, **vae.engine_config())
+    B, H, W = 2, 64, 32
+    x = torch.zeros((B, H, W, 8), dtype=torch.bfloat16)
+    mom, feats = vae.encode_nhwc(x, nhwc=True)
+    compare(record.RECORD, e.trace(eng.MODULE_VAE_ENCODE, B, H, W), "VAE encode")
+    # EMASC on the retained features (hubconf.py:41-42 channel plan), then decode with the skips
+    ein, eout = S.emasc_channels(S.SMALL_VAE["block_out_channels"])
+    em = EMASC(ein, eout)
+    em._sd = S.random_state_dict(S.emasc_param_shapes(ein, eout), 3)
+    em.device = torch.device("cpu"); em._pack()
+    W_ = {}
+    for i, (w1, b1, w2, b2) in enumerate(em.P):
+        W_.update({f"emasc.{i}.w1": w1, f"emasc.{i}.b1": b1, f"emasc.{i}.w2": w2, f"emasc.{i}.b2": b2})
+    ee = eng.Engine(W_, plan_only=True, emasc_scales=5, emasc_in=ein, emasc_out=eout, emasc_stride=[1, 1, 2, 4, 8])
+    record.RECORD.clear()
+    sel = [feats[i] if i != 2 else feats[i].clone() for i in range(1, 6)]  # (features 1 and 2 are one tensor; the plan walk uses five distinct operands)
+    inter = em(sel, None)
+    compare(record.RECORD, ee.trace(eng.MODULE_EMASC, B, H, W), "EMASC")
+    record.RECORD.clear()
+    z = torch.zeros((B, 4, H // 8, W // 8))
+    vae.decode_nhwc(z, inter, [1, 2, 3, 4, 5])
+    recs = [r for r in record.RECORD if r[0] != "ladi_nchw_f32_to_nhwc_bf16"]  # the latent layout kernel stays on the Python side of the ABI
+    compare(recs, e.trace(eng.MODULE_VAE_DECODE, B, H // 8, W // 8), "VAE decode")
+
+
+def test_adapter_sequence_matches_python(record):
+    from ladi_vton_b200 import InversionAdapter, engine as eng, synthetic as S
+    ad = InversionAdapter(input_dim=128, hidden_dim=256, output_dim=512, heads=2, mlp_dim=256)
+    ad._sd = S.random_state_dict(ad.param_shapes(), 4)
+    ad.device = torch.device("cpu"); ad._pack()
+    e = eng.Engine(eng.flatten(ad.P, "adapter."), plan_only=True, adapter_dim=128, adapter_heads=2, adapter_mlp=256, adapter_hidden=256, adapter_out=512)
+    ad(torch.zeros((3, 17, 128)))
+    compare(record.RECORD, e.trace(eng.MODULE_ADAPTER, 3, 17, 0), "inversion adapter")
+
+
+def test_engine_errors_and_workspace_monotone():
+    from ladi_vton_b200 import engine as eng, lib
+    e = eng.Engine({}, plan_only=True, unet_channels=[64, 128, 256, 256], unet_heads=[1, 2, 4, 4], unet_down_attn=[1, 1, 1, 0], unet_up_attn=[0, 1, 1, 1],
+                   unet_layers_per_block=2, unet_in_channels=31, unet_out_channels=4, unet_norm_eps=1e-5, norm_groups=32, fuse_upsample=1)
+    assert lib.load().ladi_workspace_bytes(e.h, eng.MODULE_UNET, 2, 16, 8) == -1  # no weights in the table
+    assert b"not in the table" in lib.load().ladi_last_error()
+    assert lib.load().ladi_workspace_bytes(e.h, 99, 1, 8, 8) == -1
+    assert lib.load().ladi_unet_forward(None, None, None, None, None, 1, 1, 1, 1, None, None, 0, None) != 0

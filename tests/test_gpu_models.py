@@ -460,3 +460,109 @@ def test_pipeline_device_inputs_flags_and_shape_switch(cuda, small):
         pipe(image=bad["image"], mask_image=bad["mask_image"], pose_map=bad["pose_map"], warped_cloth=bad["warped_cloth"],
              prompt_embeds=bad["prompt_embeds"], negative_prompt_embeds=bad["negative_prompt_embeds"], height=128, width=64,
              num_images_per_prompt=2)
+
+
+# ------------------------------------------------------------------------------------------------ module-level C ABI (csrc/engine.cu)
+def test_engine_abi_unet_forward_and_denoise_loop(cuda):
+    """The module-level entry points called through ctypes with raw device pointers (what a non-Python host binds): ladi_unet_forward must
+    reproduce the Python sequencing of the same kernels BIT FOR BIT (same launches, same order) and match the fp32 oracle; ladi_denoise_loop
+    (N x (UNet + CFG + DDIM) enqueued by C++) must equal N replays of the pipeline's captured step."""
+    import ctypes as C
+    from ladi_vton_b200 import DDIMScheduler, UNet2DConditionModel, engine as eng, lib, ops, synthetic as S, unet_param_shapes
+    from ladi_oracle.unet import UNet2DConditionModel as OU
+    sd = S.random_state_dict(unet_param_shapes(S.SMALL_UNET), 1234)
+    unet = UNet2DConditionModel(**S.SMALL_UNET).load_state_dict(sd).to(cuda)
+    assert unet.engine is not None
+    B, h, w = 2, 16, 8
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((2 * B, 31, h, w), generator=g)
+    ctx = torch.randn((2 * B, 77, 128), generator=g)
+    steps = unet.plan_steps([801, 601, 401])
+    kv = unet.plan_context(ctx.to(cuda))
+    xin = torch.zeros((2 * B, h, w, unet.in_pitch), dtype=torch.bfloat16, device=cuda)
+    ops.nchw_to_nhwc(x.to(cuda), xin)
+    step = torch.tensor([1, 0], dtype=torch.int32, device=cuda)
+    l = lib.load()
+    e = unet.engine
+    nbytes = l.ladi_workspace_bytes(e.h, eng.MODULE_UNET, 2 * B, h, w)
+    assert nbytes > 0
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=cuda)
+    eps = torch.empty((2 * B, h, w, 4), dtype=torch.float32, device=cuda)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = l.ladi_unet_forward(e.h, C.c_void_p(xin.data_ptr()), C.c_void_p(step.data_ptr()), C.c_void_p(steps.data_ptr()), C.c_void_p(kv.data_ptr()),
+                             2 * B, h, w, 77, C.c_void_p(eps.data_ptr()), C.c_void_p(ws.data_ptr()), nbytes, st)
+    assert rc == 0, l.ladi_last_error()
+    torch.cuda.synchronize()
+    ops.PROFILE = []  # forces the Python sequencing of the same kernels
+    try:
+        eps_py = unet.forward_nhwc(xin, step)
+    finally:
+        ops.PROFILE = None
+    assert torch.equal(eps, eps_py)
+    ou = OU(**S.SMALL_UNET).eval(); ou.load_state_dict(sd)
+    with torch.no_grad():
+        ref = ou(x, torch.tensor(601), ctx).sample
+    assert rel_l2(eps.permute(0, 3, 1, 2), ref) < 2e-2
+    # a workspace that is too small is reported, not overrun
+    rc = l.ladi_unet_forward(e.h, C.c_void_p(xin.data_ptr()), C.c_void_p(step.data_ptr()), C.c_void_p(steps.data_ptr()), C.c_void_p(kv.data_ptr()),
+                             2 * B, h, w, 77, C.c_void_p(eps.data_ptr()), C.c_void_p(ws.data_ptr()), 4096, st)
+    assert rc != 0 and b"workspace too small" in l.ladi_last_error()
+    # ---- ladi_denoise_loop: 3 steps enqueued by C++ == 3 x (forward_nhwc + ddim_cfg_step)
+    sch = DDIMScheduler(); sch.set_timesteps(3)
+    coef = sch.coefficients().to(cuda)
+    lat0 = torch.randn((B, 4, h, w), generator=g).to(cuda)
+
+    def fresh():
+        u = xin.clone()
+        lat = lat0.clone()
+        for half in (u[:B], u[B:]):
+            ops.nchw_to_nhwc(lat, half, c_off=0)
+        return u, lat, torch.zeros(2, dtype=torch.int32, device=cuda)
+    u1, lat1, s1 = fresh()
+    scratch = torch.empty((2 * B, h, w, 4), dtype=torch.float32, device=cuda)
+    rc = l.ladi_denoise_loop(e.h, C.c_void_p(u1.data_ptr()), C.c_void_p(lat1.data_ptr()), C.c_void_p(s1.data_ptr()), C.c_void_p(steps.data_ptr()),
+                             C.c_void_p(coef.data_ptr()), C.c_void_p(kv.data_ptr()), B, h, w, 77, 1, 7.5, 3, C.c_void_p(scratch.data_ptr()),
+                             C.c_void_p(ws.data_ptr()), nbytes, st)
+    assert rc == 0, l.ladi_last_error()
+    u2, lat2, s2 = fresh()
+    for _ in range(3):
+        ops.ddim_cfg_step(unet.forward_nhwc(u2, s2), lat2, u2, True, 7.5, coef, s2)
+    torch.cuda.synchronize()
+    assert s1.tolist() == [3, 0] and torch.equal(lat1, lat2) and torch.equal(u1, u2)
+
+
+def test_engine_abi_equals_python_sequencing_vae_emasc_adapter(cuda, small):
+    """ladi_vae_encode / ladi_emasc_forward / ladi_vae_decode_emasc / ladi_inversion_adapter_forward (C++ launch sequences) against the Python
+    sequencing of the same kernels: bit-identical outputs."""
+    from ladi_vton_b200 import InversionAdapter, ops, synthetic as S
+    pipe = small[0]
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand((2, 3, 128, 64), generator=g) * 2 - 1).to(cuda)
+    mask = torch.zeros((2, 1, 128, 64), device=cuda); mask[:, :, 30:100, 10:50] = 1
+    z = torch.randn((2, 4, 16, 8), generator=g).to(cuda)
+
+    def run():
+        mom, f = pipe.vae.encode_nhwc(x)
+        sel = [f[i] for i in range(1, 6)]
+        inter = pipe.emasc(sel, [ops.inv_mask_rows(mask, 128 // t.shape[1]) for t in sel])
+        img = pipe.vae.decode_nhwc(z, inter, [1, 2, 3, 4, 5])
+        return [mom] + [t.clone() for t in f[1:]] + [t.clone() for t in inter] + [img]
+    assert pipe.vae.engine is not None and pipe.emasc.engine is not None
+    a = run()
+    ops.PROFILE = []
+    try:
+        b = run()
+    finally:
+        ops.PROFILE = None
+    for i, (s, t) in enumerate(zip(a, b)):
+        assert torch.equal(s, t), f"output {i} of the C++ sequence differs from the Python sequencing"
+    ad = InversionAdapter(input_dim=128, hidden_dim=256, output_dim=512, heads=2, mlp_dim=256)
+    ad.load_state_dict(S.random_state_dict(ad.param_shapes(), 4)).to(cuda)
+    feats = torch.randn((3, 17, 128), generator=g)
+    y = ad(feats)
+    ops.PROFILE = []
+    try:
+        y2 = ad(feats)
+    finally:
+        ops.PROFILE = None
+    assert ad.engine is not None and torch.equal(y, y2)

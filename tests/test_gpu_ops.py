@@ -392,7 +392,7 @@ def test_attention_d512(cuda, D, B, nq, nkv):
 
 
 # ------------------------------------------------------------------------------------------------ fused nearest-2x upsample + conv3x3
-@pytest.mark.parametrize("n,h,w,ci,co,pair", [(2, 8, 6, 64, 64, None), (2, 8, 6, 96, 160, None), (16, 8, 6, 128, 256, None), (1, 16, 12, 320, 320, True),
+@pytest.mark.parametrize("n,h,w,ci,co,pair", [(2, 8, 6, 64, 64, None), (2, 8, 6, 96, 160, None), (16, 8, 6, 128, 256, None), (8, 16, 12, 320, 320, True),
                                                (3, 4, 4, 64, 72, None), (2, 32, 24, 128, 128, None), (1, 64, 48, 256, 256, None)])
 def test_conv_up2x(cuda, n, h, w, ci, co, pair):
     """Upsample2D (F.interpolate(scale_factor=2, nearest) + conv3x3) as one sub-pixel convolution over the half-resolution tensor."""

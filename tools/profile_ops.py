@@ -11,7 +11,8 @@ import torch  # noqa: E402
 from ladi_vton_b200 import ops, synthetic as S  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-H, W = 512, 384
+H, W = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (512, 384)
+OUT = sys.argv[4] if len(sys.argv) > 4 else "op_profile.txt"
 dev = torch.device("cuda:0")
 pipe, _ = S.build_pipeline(dev)
 inp = {k: v.to(dev) for k, v in S.synthetic_inputs(B, H, W).items()}
@@ -41,16 +42,17 @@ def table(title, prof, f):
 
 
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-with open(os.path.join(ROOT, "gpurun_out", "op_profile.txt"), "w") as f:
-    s = pipe._sessions[(B, 2 * B, H // 8, W // 8)]
+with open(os.path.join(ROOT, "gpurun_out", OUT), "w") as f:
+    s = next(iter(pipe._sessions.values()))
+    pipe.unet._ctx = s.ctx_kv
     ops.PROFILE = []
     pipe.unet.forward_nhwc(s.unet_in, s.step)
     torch.cuda.synchronize()
-    table(f"UNet forward, UNet batch {2 * B}, latents 64x48", ops.PROFILE, f)
+    table(f"UNet forward, UNet batch {2 * B}, latents {H // 8}x{W // 8}", ops.PROFILE, f)
     ops.PROFILE = []
     mom, feats = pipe.vae.encode_nhwc(inp["image"])
     torch.cuda.synchronize()
-    table(f"VAE encode, batch {B}, 512x384", ops.PROFILE, f)
+    table(f"VAE encode, batch {B}, {H}x{W}", ops.PROFILE, f)
     ops.PROFILE = []
     sel = [feats[i] for i in range(1, 6)]
     inter = pipe.emasc(sel, [ops.inv_mask_rows(inp["mask_image"], H // t.shape[1]) for t in sel])
@@ -61,4 +63,4 @@ with open(os.path.join(ROOT, "gpurun_out", "op_profile.txt"), "w") as f:
     torch.cuda.synchronize()
     table(f"VAE decode, batch {B}", ops.PROFILE, f)
     ops.PROFILE = None
-print(open(os.path.join(ROOT, "gpurun_out", "op_profile.txt")).read()[:6000])
+print(open(os.path.join(ROOT, "gpurun_out", OUT)).read()[:9000])

@@ -423,6 +423,158 @@ __device__ __forceinline__ void softmax_pair_lazy(const AttnParams& p, int n_til
   }
 }
 
+// EXPERIMENT (variant 6, not the default): softmax_pair_lazy with the two query tiles' exponential phases taking turns on the MUFU pipe
+// (named-barrier token, ids 3 / 4) and 16-column TMEM reads double-buffered under the exponentials.  Round-2 measurements
+// (profiles/r02_attn_experiments.txt): the same 331 us as variant 5 at 16 x 5 x 3072 tokens, and timing-only builds of this function
+// showed why -- with the exponentials REMOVED the kernel still takes 281 us (-15 %), without the running-maximum FMNMX 313 us, without the
+// in-phase TMEM reads 322 us: the d = 64 kernel is not MUFU-bound but bound by the per-KV-tile dependency chain softmax -> p_full ->
+// MMA issue (~350 clk for S(j+1)) -> s_full -> TMEM read, with issue slots (57 %) and MUFU (60 %) both only moderately busy.  The way
+// down is fewer instructions per score (packed f16x2 exponentials writing P directly, row sums from a ones column through the tensor
+// core), not MUFU scheduling.
+__device__ __forceinline__ void softmax_pair_pingpong(const AttnParams& p, int n_tiles, uint32_t tS, uint32_t tO, uint32_t tP, uint32_t s_full,
+                                                      uint32_t p_full, uint32_t o_ready, int ew, int lane, int q0, int h, int b, int half,
+                                                      float* xm, uint32_t wg, bool pp) {
+  constexpr int COLS = BKV / 2, OCOLS = HD / 2;
+  const uint32_t bar_id = 1 + wg, tok_mine = 3 + wg, tok_other = 4 - wg;
+  const int r = ew * 32 + lane;
+  const uint32_t lane_off = (uint32_t)(ew * 32) << 16;
+  const int col0 = half * COLS;
+  const uint32_t ts = tS + lane_off + col0;
+  const uint32_t tp = tP + lane_off + half * (COLS / 2);
+  float m = -INFINITY, l = 0.f, alpha_pending = 1.f;
+  bool rescale_pending = false;
+  const bool trace_ok = (ew == 0 && lane == 0);
+  int trace_base = 0;
+  if (pp && wg == 1) ptx::named_barrier_arrive(3, 512);  // prime: tile A owns the first turn
+  for (int j = 0; j < n_tiles; ++j) {
+    const int valid = min(COLS, p.nkv - j * BKV - col0);  // may be <= 0 for the upper half of a ragged last tile
+    trace_base = 1024 * (int)(bar_id * 2 + half) + 8 * j;
+    TRACE(0);
+    ptx::mbar_wait(s_full, j & 1);
+    ptx::tc_fence_after();
+    TRACE(1);
+    uint32_t va[16], vb[16];  // 16-column TMEM reads, double-buffered: the next read is in flight under the current exponentials
+    if (j == 0) {  // exact maximum for the first tile (one extra pass over the 64 columns)
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < COLS; c += 16) {
+        if (c >= valid) break;
+        ptx::tmem_ld16(ts + c, va);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c + i < valid) mx = fmaxf(mx, __uint_as_float(va[i]));
+      }
+      xm[half * 128 + r] = mx;
+      ptx::named_barrier_sync(bar_id, 256);
+      m = fmaxf(mx, xm[(half ^ 1) * 128 + r]) * p.scale_log2;
+    } else {
+      ptx::mbar_wait(o_ready, (j - 1) & 1);  // P(j-1) V(j-1) done: the P region and O are free (issued right behind S(j): long complete)
+      ptx::tc_fence_after();
+      if (__any_sync(0xffffffffu, rescale_pending)) {  // the reference moved at the last boundary: bring O to the new scale
+        uint32_t o[32];
+        ptx::tmem_ld32(tO + lane_off + half * OCOLS, o);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha_pending);
+        ptx::tmem_st32(tO + lane_off + half * OCOLS, o);
+      }
+    }
+    if (0 < valid) ptx::tmem_ld16(ts, va);
+    ptx::tmem_wait_ld();
+    TRACE(2);
+    // ---------------------------------------------------------------- this tile's turn on the MUFU pipe
+    if (pp) ptx::named_barrier_sync(tok_mine, 512);
+    TRACE(3);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    float x0 = -INFINITY, x1 = -INFINITY, x2 = -INFINITY, x3 = -INFINITY;
+    auto sub = [&](const uint32_t (&v)[16], int c) {  // 16 keys -> 8 packed columns of P
+      uint32_t pk[8];
+      if (c + 16 <= valid) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float a0 = __uint_as_float(v[i]), a1 = __uint_as_float(v[i + 1]), a2 = __uint_as_float(v[i + 2]), a3 = __uint_as_float(v[i + 3]);
+          x0 = fmaxf(x0, a0); x1 = fmaxf(x1, a1); x2 = fmaxf(x2, a2); x3 = fmaxf(x3, a3);
+          const float p0 = ex2(fmaf(a0, p.scale_log2, -m)), p1 = ex2(fmaf(a1, p.scale_log2, -m));
+          const float p2 = ex2(fmaf(a2, p.scale_log2, -m)), p3 = ex2(fmaf(a3, p.scale_log2, -m));
+          s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+          pk[i >> 1] = ptx::pack_bf16(p0, p1);
+          pk[(i >> 1) + 1] = ptx::pack_bf16(p2, p3);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          float p0 = 0.f, p1 = 0.f;
+          if (c + i < valid) { const float a = __uint_as_float(v[i]); x0 = fmaxf(x0, a); p0 = ex2(fmaf(a, p.scale_log2, -m)); }
+          if (c + i + 1 < valid) { const float a = __uint_as_float(v[i + 1]); x1 = fmaxf(x1, a); p1 = ex2(fmaf(a, p.scale_log2, -m)); }
+          s0 += p0; s1 += p1;
+          pk[i >> 1] = ptx::pack_bf16(p0, p1);
+        }
+      }
+      ptx::tmem_st8(tp + (c >> 1), pk);
+    };
+    if (16 < valid) ptx::tmem_ld16(ts + 16, vb);
+    sub(va, 0);
+    ptx::tmem_wait_ld();
+    if (32 < valid) ptx::tmem_ld16(ts + 32, va);
+    sub(vb, 16);
+    TRACE(4);
+    ptx::tmem_wait_ld();
+    if (48 < valid) ptx::tmem_ld16(ts + 48, vb);
+    sub(va, 32);
+    ptx::tmem_wait_ld();
+    if (pp && !(wg == 1 && j == n_tiles - 1)) {
+      // the last 16 exponentials of this tile overlap the other tile's start; the hand-over is a named-barrier arrival (non-blocking)
+      ptx::named_barrier_arrive(tok_other, 512);
+    }
+    sub(vb, 48);
+    TRACE(5);
+    l += (s0 + s1) + (s2 + s3);
+    ptx::tmem_wait_st();
+    ptx::tc_fence_before();
+    ptx::mbar_arrive(p_full);
+    TRACE(6);
+    // ---- off the MMA critical path, under the OTHER tile's exponentials: agree on the reference for the next tile
+    if (j + 1 < n_tiles) {
+      float* slot = xm + ((j + 1) & 1) * 256;
+      const float mxl = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
+      slot[half * 128 + r] = mxl;
+      ptx::named_barrier_sync(bar_id, 256);
+      const float m_true = fmaxf(mxl, slot[(half ^ 1) * 128 + r]) * p.scale_log2;
+      rescale_pending = m_true > m + 8.f;
+      alpha_pending = rescale_pending ? ex2(m - m_true) : 1.f;
+      if (rescale_pending) { l *= alpha_pending; m = m_true; }
+    }
+    TRACE(7);
+  }
+  // ---- output: O / l, row sum = sum over both column halves (identical references throughout)
+  {
+    float* slot = xm + ((n_tiles + 1) & 1) * 256;
+    slot[half * 128 + r] = l;
+    ptx::named_barrier_sync(bar_id, 256);
+    l += slot[(half ^ 1) * 128 + r];
+  }
+  ptx::mbar_wait(o_ready, (n_tiles - 1) & 1);
+  ptx::tc_fence_after();
+  const int qi = q0 + r;
+  const float inv = 1.f / l;
+  bf16* orow = p.out + (size_t)b * p.out_batch_stride + (size_t)qi * p.out_pitch + h * HD + half * OCOLS;
+  uint32_t v[32];
+  ptx::tmem_ld32(tO + lane_off + half * OCOLS, v);
+  ptx::tmem_wait_ld();
+  if (qi < p.nq) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      uint4 u;
+      u.x = ptx::pack_bf16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+      u.y = ptx::pack_bf16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+      u.z = ptx::pack_bf16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+      u.w = ptx::pack_bf16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+      *reinterpret_cast<uint4*>(orow + i) = u;
+    }
+  }
+}
+
 __device__ __forceinline__ void issue_qk(uint32_t tS, uint64_t qdesc, uint64_t kdesc) {
   constexpr uint32_t idesc_qk = ptx::idesc_bf16(128, BKV, 0, 0);
 #pragma unroll
@@ -551,7 +703,7 @@ attention_single_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 // versa, so MMA latency is hidden instead of being added to every iteration.  K/V ring of 3 stages (tile t is needed from
 // S_A(t), issued in iteration t-1, until PV_B(t), issued in iteration t+1).
 constexpr int PAIR_KV_STAGES = 3;
-template <bool SR, bool PT, bool LAZY = false>
+template <bool SR, bool PT, bool LAZY = false, bool PINGPONG = false>
 __global__ void __launch_bounds__(640, 1)
 attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
@@ -678,7 +830,10 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int wg = (warp - 4) >> 3;         // 0 = tile A (warps 4-11), 1 = tile B (warps 12-19)
     const int half = ((warp - 4) >> 2) & 1;  // which half of the key columns / O columns this warpgroup owns
     if (wg == 0 || has_b) {
-      if constexpr (LAZY)
+      if constexpr (PINGPONG)
+        softmax_pair_pingpong(p, n_tiles, tmem_base + 128 * wg, tmem_base + 256 + 64 * wg, tmem_base + 384 + 64 * wg, s_full0 + 8 * wg,
+                              p_full0 + 8 * wg, o_ready0 + 8 * wg, warp & 3, lane, (qp * 2 + wg) * BQ, h, b, half, xm + wg * 512, (uint32_t)wg, has_b);
+      else if constexpr (LAZY)
         softmax_pair_lazy(p, n_tiles, tmem_base + 128 * wg, tmem_base + 256 + 64 * wg, tmem_base + 384 + 64 * wg, s_full0 + 8 * wg,
                           p_full0 + 8 * wg, o_ready0 + 8 * wg, warp & 3, lane, (qp * 2 + wg) * BQ, h, b, half, xm + wg * 512, 1 + wg);
       else
@@ -1006,6 +1161,7 @@ extern "C" int ladi_attention_bf16(const ladi_attn_desc* d, void* stream_) {
     LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
     LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
     LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
+    LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
     attr_set = true;
   }
   // variant: 0 auto, 1 one query tile per CTA, 2 pair (P in smem), 4 pair (P in tensor memory), 5 pair (P in TMEM + lazy single-pass softmax)
@@ -1021,6 +1177,7 @@ extern "C" int ladi_attention_bf16(const ladi_attn_desc* d, void* stream_) {
     dim3 grid((d->nq + 2 * BQ - 1) / (2 * BQ), d->heads, d->batch);
     if (variant == 4) LADI_CUDA(ladi_launch(attention_pair_kernel<false, true>, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
     else if (variant == 5) LADI_CUDA(ladi_launch(attention_pair_kernel<false, true, true>, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
+    else if (variant == 6) LADI_CUDA(ladi_launch(attention_pair_kernel<false, true, true, true>, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
     else LADI_CUDA(ladi_launch(attention_pair_kernel<false, false>, grid, dim3(640), SMEM_PAIR, stream, tq, tk, tv, p));
   }
   return LADI_OK;

@@ -546,7 +546,7 @@ def test_engine_abi_equals_python_sequencing_vae_emasc_adapter(cuda, small):
         sel = [f[i] for i in range(1, 6)]
         inter = pipe.emasc(sel, [ops.inv_mask_rows(mask, 128 // t.shape[1]) for t in sel])
         img = pipe.vae.decode_nhwc(z, inter, [1, 2, 3, 4, 5])
-        return [mom] + [t.clone() for t in f[1:]] + [t.clone() for t in inter] + [img]
+        return [mom] + [t.clone() for t in f[1:]] + [t.clone() for t in inter] + [img[..., :3].clone()]  # (channel 3 of the image buffer is padding)
     assert pipe.vae.engine is not None and pipe.emasc.engine is not None
     a = run()
     ops.PROFILE = []

@@ -229,8 +229,8 @@ def test_conv_invalid_args_error(cuda):
 
 # ------------------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("B,heads,nq,nkv", [(2, 5, 768, 768), (1, 2, 128, 128), (2, 3, 192, 192), (3, 2, 48, 48), (2, 5, 768, 77),
-                                            (1, 1, 3072, 3072), (2, 2, 200, 333)])
-@pytest.mark.parametrize("variant", [0, 1, 2, 4, 5])
+                                            (1, 1, 3072, 3072), (2, 2, 200, 333), (2, 3, 384, 640)])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 5, 6])
 def test_attention(cuda, B, heads, nq, nkv, variant):
     from ladi_vton_b200 import ops
     C = heads * 64

@@ -18,7 +18,8 @@ t = tr.cpu().numpy().astype("int64")
 t0 = t[t > 0].min()
 names = {2: "A.half0", 3: "A.half1", 4: "B.half0", 5: "B.half1"}
 for k, nm in names.items():
-    print(f"== softmax {nm}: per tile [wait s_full | ld0 | math0+st0 | ld1 | math1+st1 | wait st+arrive | max exchange] (cycles), start rel")
+    print(f"== softmax {nm}: per tile (variant 5) [wait s_full | ld0 | math0+st0 | ld1 | math1+st1 | wait st+arrive | max exchange]; (variant 6) "
+          f"[wait s_full | first ld + o_ready | wait token | exps 0-31 | exps 32-63 | st+arrive | max exchange] (cycles), start rel")
     tot = []
     for j in range(0, 24):
         s = t[1024 * k + 8 * j: 1024 * k + 8 * j + 8]

@@ -1,0 +1,94 @@
+// Micro-benchmark of the attention softmax inner loop in isolation (registers only; no TMEM, no barriers): cycles per score per SM
+// sub-partition for three formulations, at 2 and 4 warps per sub-partition (the pair kernel runs 4).
+//   A: current -- fp32 FFMA, MUFU.EX2 (f32), FADD row sum, FMNMX running max, F2FP bf16x2 pack; 16 scores per batch
+//   B: the same with 32 scores per batch
+//   C: packed -- fp32 FFMA, cvt.rn.f16x2.f32, ex2.approx.f16x2 (P comes out packed), HADD2 partial row sums, HMNMX2 running max
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o softmax_loop softmax_loop.cu ; ./softmax_loop
+#include <cstdio>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+__device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ uint32_t ex2h2(uint32_t x) { uint32_t y; asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+__device__ __forceinline__ uint32_t cvt_h2(float lo, float hi) { uint32_t y; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo)); return y; }
+__device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t b) { uint32_t y; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b)); return y; }
+__device__ __forceinline__ uint32_t hmax2(uint32_t a, uint32_t b) { uint32_t y; asm("max.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b)); return y; }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) { __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&t); }
+
+template <int MODE, int BATCH>
+__global__ void __launch_bounds__(512, 1) loop(uint32_t* out, int iters, float scale, float m, long long* cycles) {
+  float v[BATCH];
+#pragma unroll
+  for (int i = 0; i < BATCH; ++i) v[i] = (float)((threadIdx.x * 7 + i * 13) % 97) * 0.05f - 2.f;
+  uint32_t acc = 0;
+  float s0 = 0, s1 = 0, s2 = 0, s3 = 0, x0 = -1e30f, x1 = -1e30f, x2 = -1e30f, x3 = -1e30f;
+  uint32_t hs0 = 0, hs1 = 0, hm = 0xfbfffbffu;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    if (MODE == 0) {
+      uint32_t pk[BATCH / 2];
+#pragma unroll
+      for (int i = 0; i < BATCH; i += 4) {
+        const float a0 = v[i], a1 = v[i + 1], a2 = v[i + 2], a3 = v[i + 3];
+        x0 = fmaxf(x0, a0); x1 = fmaxf(x1, a1); x2 = fmaxf(x2, a2); x3 = fmaxf(x3, a3);
+        const float p0 = ex2f(fmaf(a0, scale, -m)), p1 = ex2f(fmaf(a1, scale, -m)), p2 = ex2f(fmaf(a2, scale, -m)), p3 = ex2f(fmaf(a3, scale, -m));
+        s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+        pk[i >> 1] = pack_bf16(p0, p1); pk[(i >> 1) + 1] = pack_bf16(p2, p3);
+      }
+#pragma unroll
+      for (int i = 0; i < BATCH / 2; ++i) acc ^= pk[i];
+    } else {
+      uint32_t pk[BATCH / 2];
+#pragma unroll
+      for (int i = 0; i < BATCH; i += 2) {
+        const uint32_t h = cvt_h2(fmaf(v[i], scale, -m), fmaf(v[i + 1], scale, -m));
+        hm = hmax2(hm, h);
+        const uint32_t e = ex2h2(h);
+        if (i & 2) hs1 = hadd2(hs1, e); else hs0 = hadd2(hs0, e);
+        pk[i >> 1] = e;
+      }
+#pragma unroll
+      for (int i = 0; i < BATCH / 2; ++i) acc ^= pk[i];
+    }
+    // new "scores" for the next batch (cheap, keeps the compiler from hoisting): rotate + perturb with the accumulated bits
+#pragma unroll
+    for (int i = 0; i < BATCH; ++i) v[i] = __uint_as_float((__float_as_uint(v[i]) & 0xfffffff0u) | ((acc >> (i & 15)) & 3u));
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc ^ __float_as_uint(s0 + s1 + s2 + s3 + x0 + x1 + x2 + x3) ^ hs0 ^ hs1 ^ hm;
+}
+
+template <int MODE, int BATCH>
+void run(const char* name, int threads) {
+  int sms;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  uint32_t* out; long long* cyc;
+  cudaMalloc(&out, sms * 512 * 4); cudaMalloc(&cyc, sms * 8);
+  const int iters = 2000;
+  loop<MODE, BATCH><<<sms, threads>>>(out, 10, 1.4427f * 0.125f, 1.f, cyc);
+  loop<MODE, BATCH><<<sms, threads>>>(out, iters, 1.4427f * 0.125f, 1.f, cyc);
+  cudaDeviceSynchronize();
+  long long h[256];
+  cudaMemcpy(h, cyc, sms * 8, cudaMemcpyDeviceToHost);
+  double mean = 0;
+  for (int i = 0; i < sms; ++i) mean += h[i];
+  mean /= sms;
+  const double scores_per_smsp = (double)threads / 4 * iters * BATCH;  // scores processed by one sub-partition's warps
+  printf("%-44s %2d warps/SMSP: %7.2f clk per warp-wide score row per SMSP  (%5.1f scores/clk/SM; 64x128-score tile for 2 query tiles: %6.0f clk)\n", name, threads / 128,
+         mean / (scores_per_smsp / 32), (double)threads * iters * BATCH / mean, mean / (scores_per_smsp / 32) * (2.0 * 128 * 128 / 4 / 32));
+  cudaFree(out); cudaFree(cyc);
+}
+
+int main() {
+  for (int th : {256, 512}) {
+    run<0, 16>("A  f32 ex2 + FADD + FMNMX + bf16 pack, batch 16", th);
+    run<0, 32>("B  same, batch 32", th);
+    run<1, 16>("C  cvt.f16x2 + ex2.f16x2 + HADD2 + HMNMX2, batch 16", th);
+    run<1, 32>("C  same, batch 32", th);
+  }
+  return 0;
+}

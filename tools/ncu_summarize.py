@@ -45,7 +45,7 @@ conv_traffic = []
 for r in rows[i0 + 2:]:
     if len(r) <= col["Kernel Name"]:
         continue
-    name = re.sub(r"\(.*", "", r[col["Kernel Name"]]).replace("(anonymous namespace)::", "").replace("void ", "")
+    name = re.sub(r"\(.*", "", r[col["Kernel Name"]]).replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("void ", "")
     us = to_us(r)
     rd, wr = to_bytes(r, "dram__bytes_read.sum"), to_bytes(r, "dram__bytes_write.sum")
     gbs = (rd + wr) / (us * 1e-6) / 1e9 if us > 0 else 0

@@ -15,6 +15,40 @@ __device__ __forceinline__ uint32_t ex2h2(uint32_t x) { uint32_t y; asm("ex2.app
 __device__ __forceinline__ uint32_t cvt_h2(float lo, float hi) { uint32_t y; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(hi), "f"(lo)); return y; }
 __device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t b) { uint32_t y; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b)); return y; }
 __device__ __forceinline__ uint32_t hmax2(uint32_t a, uint32_t b) { uint32_t y; asm("max.f16x2 %0, %1, %2;" : "=r"(y) : "r"(a), "r"(b)); return y; }
+// 2^x on the FMA pipe (no MUFU): round-to-nearest integer part through the 1.5*2^23 magic add, degree-3 minimax polynomial on the
+// fraction in [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding of P), exponent inserted with one integer multiply-add
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(0.055171654f, f, 0.24261113f);
+  p = fmaf(p, f, 0.69326097f);
+  p = fmaf(p, f, 0.99992806f);
+  return __int_as_float(__float_as_int(t) * (1 << 23) + __float_as_int(p));
+}
+// the same for TWO scores with packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2)
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& r0, float& r1) {
+  x0 = fmaxf(x0, -125.f); x1 = fmaxf(x1, -125.f);
+  uint64_t x, t, f, p, magic, nmagic, c3, c2, c1, c0;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(magic) : "f"(12582912.f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(nmagic) : "f"(-12582912.f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c3) : "f"(0.055171654f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(0.24261113f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c1) : "f"(0.69326097f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c0) : "f"(0.99992806f));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(x), "l"(magic));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(f) : "l"(t), "l"(nmagic));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(f) : "l"(x), "l"(f));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(c3), "l"(f), "l"(c2));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(p), "l"(f), "l"(c1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(p), "l"(f), "l"(c0));
+  float t0, t1, p0, p1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(t));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(p0), "=f"(p1) : "l"(p));
+  r0 = __int_as_float(__float_as_int(t0) * (1 << 23) + __float_as_int(p0));
+  r1 = __int_as_float(__float_as_int(t1) * (1 << 23) + __float_as_int(p1));
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) { __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&t); }
 
 template <int MODE, int BATCH>
@@ -39,7 +73,24 @@ __global__ void __launch_bounds__(512, 1) loop(uint32_t* out, int iters, float s
         pk[i >> 1] = pack_bf16(p0, p1); pk[(i >> 1) + 1] = pack_bf16(p2, p3);
       }
 #pragma unroll
-      for (int i = 0; i < BATCH / 2; ++i) acc ^= pk[i];
+      for (int i = 0; i < BATCH / 2; ++i) asm volatile("" ::"r"(pk[i]));
+    } else if (MODE == 2 || MODE == 3 || MODE == 4) {
+      // D / E / F: of every 4 scores, POLY of them go through the FMA-pipe polynomial (D: 2 scalar, E: 2 packed f32x2, F: 1 scalar), the rest through MUFU
+      uint32_t pk[BATCH / 2];
+#pragma unroll
+      for (int i = 0; i < BATCH; i += 4) {
+        const float a0 = v[i], a1 = v[i + 1], a2 = v[i + 2], a3 = v[i + 3];
+        x0 = fmaxf(x0, a0); x1 = fmaxf(x1, a1); x2 = fmaxf(x2, a2); x3 = fmaxf(x3, a3);
+        const float p0 = ex2f(fmaf(a0, scale, -m));
+        float p1, p2, p3;
+        if (MODE == 2) { p1 = exp2_poly(fmaf(a1, scale, -m)); p2 = ex2f(fmaf(a2, scale, -m)); p3 = exp2_poly(fmaf(a3, scale, -m)); }
+        else if (MODE == 3) { p2 = ex2f(fmaf(a2, scale, -m)); exp2_poly2(fmaf(a1, scale, -m), fmaf(a3, scale, -m), p1, p3); }
+        else { p1 = ex2f(fmaf(a1, scale, -m)); p2 = ex2f(fmaf(a2, scale, -m)); p3 = exp2_poly(fmaf(a3, scale, -m)); }
+        s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+        pk[i >> 1] = pack_bf16(p0, p1); pk[(i >> 1) + 1] = pack_bf16(p2, p3);
+      }
+#pragma unroll
+      for (int i = 0; i < BATCH / 2; ++i) asm volatile("" ::"r"(pk[i]));
     } else {
       uint32_t pk[BATCH / 2];
 #pragma unroll
@@ -51,11 +102,12 @@ __global__ void __launch_bounds__(512, 1) loop(uint32_t* out, int iters, float s
         pk[i >> 1] = e;
       }
 #pragma unroll
-      for (int i = 0; i < BATCH / 2; ++i) acc ^= pk[i];
+      for (int i = 0; i < BATCH / 2; ++i) asm volatile("" ::"r"(pk[i]));
     }
-    // new "scores" for the next batch (cheap, keeps the compiler from hoisting): rotate + perturb with the accumulated bits
+    // keep the compiler from hoisting the batch out of the loop WITHOUT adding instructions (an earlier version perturbed the scores with
+    // three integer ops each and measured mostly its own scaffolding): the scores become opaque again through empty asm statements
 #pragma unroll
-    for (int i = 0; i < BATCH; ++i) v[i] = __uint_as_float((__float_as_uint(v[i]) & 0xfffffff0u) | ((acc >> (i & 15)) & 3u));
+    for (int i = 0; i < BATCH; ++i) asm volatile("" : "+f"(v[i]));
   }
   const long long t1 = clock64();
   if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
@@ -83,12 +135,37 @@ void run(const char* name, int threads) {
   cudaFree(out); cudaFree(cyc);
 }
 
+__global__ void accuracy(float* out) {  // max relative error of the polynomial against exp2f over [-30, 8]
+  float worst = 0.f, worst2 = 0.f;
+  for (int i = threadIdx.x; i < 400000; i += blockDim.x) {
+    const float x = -30.f + 38.f * (float)i / 400000.f;
+    const float ref = exp2f(x);
+    worst = fmaxf(worst, fabsf(exp2_poly(x) - ref) / ref);
+    float r0, r1;
+    exp2_poly2(x, x + 0.37f, r0, r1);
+    worst2 = fmaxf(worst2, fmaxf(fabsf(r0 - ref) / ref, fabsf(r1 - exp2f(x + 0.37f)) / exp2f(x + 0.37f)));
+  }
+  atomicMax(reinterpret_cast<int*>(out), __float_as_int(worst));
+  atomicMax(reinterpret_cast<int*>(out) + 1, __float_as_int(worst2));
+  if (threadIdx.x == 0) { out[2] = exp2_poly(-200.f); out[3] = exp2_poly(-126.5f); }
+}
+
 int main() {
+  {
+    float* d; float h[4];
+    cudaMalloc(&d, 16); cudaMemset(d, 0, 16);
+    accuracy<<<1, 256>>>(d);
+    cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    printf("polynomial exp2: max relative error vs exp2f on [-30, 8]: scalar %.3g, packed f32x2 %.3g; exp2_poly(-200) = %g, (-126.5) = %g\n", h[0], h[1], h[2], h[3]);
+  }
   for (int th : {256, 512}) {
     run<0, 16>("A  f32 ex2 + FADD + FMNMX + bf16 pack, batch 16", th);
     run<0, 32>("B  same, batch 32", th);
     run<1, 16>("C  cvt.f16x2 + ex2.f16x2 + HADD2 + HMNMX2, batch 16", th);
     run<1, 32>("C  same, batch 32", th);
+    run<2, 32>("D  A with 2 of 4 exps as FMA-pipe polynomial, b32", th);
+    run<3, 32>("E  A with 2 of 4 exps as packed f32x2 polynomial, b32", th);
+    run<4, 32>("F  A with 1 of 4 exps as FMA-pipe polynomial, b32", th);
   }
   return 0;
 }

@@ -116,7 +116,8 @@ typedef struct ladi_attn_desc {
   const void* v; int v_pitch; int64_t v_batch_stride;
   void* out; int out_pitch; int64_t out_batch_stride;
   float scale;               /* softmax(scale * q k^T) */
-  int variant;               /* 0 = auto; 1 = one query tile per CTA; 2 = two query tiles per CTA (tests / tuning) */
+  int variant;               /* 0 = auto (nkv <= 128: 8; nq >= 512: 5; else 1); 1 = one query tile per CTA; 2 / 4 / 5 / 6 = two query tiles per CTA (P in smem / in TMEM /
+                                + lazy single-pass softmax / + ping-pong experiment); 8 = persistent kernel for a single K/V tile (tests / tuning) */
   void* trace;               /* optional device int64[8192]: per-phase clock64() stamps of CTA (0,0,0) (tools/attn_trace.py); NULL */
   int head_dim;              /* ladi_attention_d512_bf16 only: 0 or 512 (the VAE), or 256 (reduced-width test models) */
 } ladi_attn_desc;

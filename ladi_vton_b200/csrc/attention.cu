@@ -12,8 +12,10 @@
 //       warp, so each tile's chain  softmax(j) -> S(j+1), P(j) V(j) -> softmax(j+1)  advances independently and the tensor core works
 //       on one tile while the other is in its softmax; S(j+1) is issued before P(j) V(j) (shortest path back to the softmax warps);
 //       K/V tiles are loaded once for both query tiles (3-stage TMA ring, released when both issuers are done with a tile).
-//   attention_single_kernel<SHORT>: one query tile per CTA; SHORT (nkv <= 128, e.g. the 77 text tokens of cross-attention)
-//       needs one K/V stage and 256 TMEM columns, so two CTAs share an SM and hide each other's latency chain.
+//   attention_single_kernel<SHORT>: one query tile per CTA; SHORT (nkv <= 128) needs one K/V stage and 256 TMEM columns, so two CTAs share
+//       an SM and hide each other's latency chain.
+//   attention_short_persistent_kernel (round 2, the default for nkv <= 128 = the 77 text tokens of cross-attention): persistent CTAs looping
+//       over (query tile, head, image) items with a two-stage TMA ring and P in tensor memory.
 //
 // Replaces diffusers CrossAttention (attn1/attn2 of BasicTransformerBlock) inside UNet2DConditionModel.forward, which the
 // reference runs through torch SDPA or xformers (/root/reference/src/inference.py:143-147; call-site tryon_pipe.py:732).
@@ -698,6 +700,184 @@ attention_single_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   }
 }
 
+// ============================================================================================ short K/V, persistent
+// Cross-attention over the 77 text tokens (attn2 of every BasicTransformerBlock; nkv <= 128 = ONE K/V tile).  The one-tile-per-CTA kernel
+// above spends most of its ~5 us per CTA on fixed costs -- barrier init, TMEM allocation, tensor-map prefetch, the first TMA round trip --
+// for 1920 CTAs per launch at the 64x48 level.  Here a CTA is persistent: it loops over (query tile, head, image) items, two-stage TMA ring for
+// Q / K / V so the loads of item i+1 fly under item i, P goes to tensor memory (no smem round trip), and two CTAs share an SM (96 KiB
+// smem, 256 TMEM columns each) so one CTA's softmax runs under the other's MMAs and loads.
+//   TMEM: S [0,128)  O [128,192)  P [192,256)       barriers: ld_full[2] ld_empty[2] s_full p_full o_full o_free
+__global__ void __launch_bounds__(256, 2)
+attention_short_persistent_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                                  const __grid_constant__ AttnParams p, int q_tiles, int heads, int items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                       // 2 stages
+  uint8_t* sK = sQ + 2 * TILE_BYTES;        // 2 stages
+  uint8_t* sV = sK + 2 * TILE_BYTES;        // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * TILE_BYTES);
+  const uint32_t b0 = ptx::smem_u32(bars);
+  const uint32_t ld_full0 = b0, ld_empty0 = b0 + 16, s_full = b0 + 32, p_full = b0 + 40, o_full = b0 + 48, o_free = b0 + 56;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ); ptx::prefetch_tmap(&tmK); ptx::prefetch_tmap(&tmV);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ld_full0 + 8 * s, 1);
+      ptx::mbar_init(ld_empty0 + 8 * s, 1);
+    }
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(p_full, 128);
+    ptx::mbar_init(o_full, 1);
+    ptx::mbar_init(o_free, 128);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 256);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + 128, tP = tmem_base + 192;
+  ptx::pdl_wait();
+
+  auto decode = [&](int item, int& qt, int& h, int& b) {  // query tile fastest: consecutive items of a CTA re-read the same K/V from L2
+    qt = item % q_tiles;
+    const int r = item / q_tiles;
+    h = r % heads;
+    b = r / heads;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      const int st = it & 1;
+      int qt, h, b;
+      decode(item, qt, h, b);
+      ptx::mbar_wait(ld_empty0 + 8 * st, ((it >> 1) & 1) ^ 1);
+      const uint32_t fb = ld_full0 + 8 * st;
+      if (ptx::elect_one()) {
+        ptx::mbar_expect_tx(fb, 3 * TILE_BYTES);
+        ptx::tma_load_3d(&tmQ, ptx::smem_u32(sQ + st * TILE_BYTES), fb, h * HD, qt * BQ, b);
+        ptx::tma_load_3d(&tmK, ptx::smem_u32(sK + st * TILE_BYTES), fb, h * HD, 0, b);
+        ptx::tma_load_3d(&tmV, ptx::smem_u32(sV + st * TILE_BYTES), fb, h * HD, 0, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    int it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      const int st = it & 1;
+      ptx::mbar_wait(ld_full0 + 8 * st, (it >> 1) & 1);
+      if (it > 0) ptx::mbar_wait(o_free, (it - 1) & 1);  // the softmax warps have read O(it-1) (hence S / P of it-1 are dead too)
+      ptx::tc_fence_after();
+      const uint64_t qd = ptx::smem_desc_sw128(ptx::smem_u32(sQ + st * TILE_BYTES));
+      const uint64_t kd = ptx::smem_desc_sw128(ptx::smem_u32(sK + st * TILE_BYTES));
+      const uint64_t vd = ptx::smem_desc_sw128(ptx::smem_u32(sV + st * TILE_BYTES));
+      if (ptx::elect_one()) {
+        issue_qk(tS, qd, kd);
+        ptx::mma_commit(s_full);
+      }
+      __syncwarp();
+      ptx::mbar_wait(p_full, it & 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        issue_pv_ts(tO, tP, vd, 1);
+        ptx::mma_commit(o_full);
+        ptx::mma_commit(ld_empty0 + 8 * st);  // Q / K / V stage reusable
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ softmax + output: one thread per query row, single K/V tile
+    const int ew = warp & 3;
+    const int r = ew * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(ew * 32) << 16;
+    const int valid = p.nkv;  // <= 128
+    int it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      int qt, h, b;
+      decode(item, qt, h, b);
+      ptx::mbar_wait(s_full, it & 1);
+      ptx::tc_fence_after();
+      // pass 1: row maximum over the valid keys
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < BKV; c += 32) {
+        if (c >= valid) break;
+        uint32_t v[32];
+        ptx::tmem_ld32(tS + lane_off + c, v);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      const float m = mx * p.scale_log2;
+      // pass 2: p = exp2(s * scale - m) packed to bf16 into tensor memory (zeros for the padding keys), row sum in fp32
+      float l = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BKV; c += 32) {
+        uint32_t v[32], pk[16];
+        if (c < valid) {
+          ptx::tmem_ld32(tS + lane_off + c, v);
+          ptx::tmem_wait_ld();
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = 0.f, p1 = 0.f;
+          if (c + i < valid) p0 = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m));
+          if (c + i + 1 < valid) p1 = ex2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m));
+          l += p0 + p1;
+          pk[i >> 1] = ptx::pack_bf16(p0, p1);
+        }
+        ptx::tmem_st16(tP + lane_off + (c >> 1), pk);
+      }
+      ptx::tmem_wait_st();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(p_full);
+      // output: O / l
+      ptx::mbar_wait(o_full, it & 1);
+      ptx::tc_fence_after();
+      const int qi = qt * BQ + r;
+      const float inv = 1.f / l;
+      bf16* orow = p.out + (size_t)b * p.out_batch_stride + (size_t)qi * p.out_pitch + h * HD;
+#pragma unroll
+      for (int c = 0; c < HD; c += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld32(tO + lane_off + c, v);
+        ptx::tmem_wait_ld();
+        if (c + 32 == HD) {  // every accumulator column is in registers: S, P and O of this item may be overwritten
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(o_free);
+        }
+        if (qi < p.nq) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 u;
+            u.x = ptx::pack_bf16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+            u.y = ptx::pack_bf16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+            u.z = ptx::pack_bf16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+            u.w = ptx::pack_bf16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + c + i) = u;
+          }
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  ptx::pdl_trigger();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 256);
+  }
+}
+constexpr size_t SMEM_SHORT_PERSIST = 6 * TILE_BYTES + 8 * 8 + 16 + 1024;
+
 // ============================================================================================ two query tiles per CTA
 // Tile B runs ONE KV tile behind tile A: while warpgroup A is in its softmax the tensor core executes B's PV / QK^T and vice
 // versa, so MMA latency is hidden instead of being added to every iteration.  K/V ring of 3 stages (tile t is needed from
@@ -1158,6 +1338,7 @@ extern "C" int ladi_attention_bf16(const ladi_attn_desc* d, void* stream_) {
   if (!attr_set) {
     LADI_CUDA(cudaFuncSetAttribute(attention_single_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SINGLE));
     LADI_CUDA(cudaFuncSetAttribute(attention_single_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SHORT));
+    LADI_CUDA(cudaFuncSetAttribute(attention_short_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_SHORT_PERSIST));
     LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
     LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
     LADI_CUDA(cudaFuncSetAttribute(attention_pair_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_PAIR));
@@ -1166,8 +1347,15 @@ extern "C" int ladi_attention_bf16(const ladi_attn_desc* d, void* stream_) {
   }
   // variant: 0 auto, 1 one query tile per CTA, 2 pair (P in smem), 4 pair (P in tensor memory), 5 pair (P in TMEM + lazy single-pass softmax)
   int variant = d->variant;
-  if (variant == 0) variant = (d->nkv <= BKV || d->nq < 512) ? 1 : 5;  // measured: the pair kernel wins from ~512 queries up
-  if (variant == 1 && d->nkv <= BKV) {
+  // auto: one K/V tile (cross-attention over the text tokens, tiny self-attention) -> the persistent short-K/V kernel (1.14-1.41x over one tile per
+  // CTA, profiles/r02_xattn_bench.jsonl); long sequences -> two query tiles per CTA from ~512 queries up
+  if (variant == 0) variant = d->nkv <= BKV ? 8 : (d->nq < 512 ? 1 : 5);
+  if (variant == 8) {
+    LADI_CHECK(d->nkv <= BKV, "variant 8 (persistent short-K/V kernel) needs nkv <= 128");
+    const int q_tiles = (d->nq + BQ - 1) / BQ, items = q_tiles * d->heads * d->batch;
+    const int grid = items < 2 * ladi_num_sms() ? items : 2 * ladi_num_sms();
+    LADI_CUDA(ladi_launch(attention_short_persistent_kernel, dim3(grid), dim3(256), SMEM_SHORT_PERSIST, stream, tq, tk, tv, p, q_tiles, d->heads, items));
+  } else if (variant == 1 && d->nkv <= BKV) {
     dim3 grid((d->nq + BQ - 1) / BQ, d->heads, d->batch);
     LADI_CUDA(ladi_launch(attention_single_kernel<true>, grid, dim3(256), SMEM_SHORT, stream, tq, tk, tv, p));
   } else if (variant == 1) {

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(512, 1) loop(uint32_t* out, int iters, float s
         pk[i >> 1] = pack_bf16(p0, p1); pk[(i >> 1) + 1] = pack_bf16(p2, p3);
       }
 #pragma unroll
-      for (int i = 0; i < BATCH / 2; ++i) asm volatile("" ::"r"(pk[i]));
+      for (int i = 0; i < BATCH / 2; ++i) acc ^= pk[i];
     } else if (MODE == 2 || MODE == 3 || MODE == 4) {
       // D / E / F: of every 4 scores, POLY of them go through the FMA-pipe polynomial (D: 2 scalar, E: 2 packed f32x2, F: 1 scalar), the rest through MUFU
       uint32_t pk[BATCH / 2];
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(512, 1) loop(uint32_t* out, int iters, float s
         pk[i >> 1] = pack_bf16(p0, p1); pk[(i >> 1) + 1] = pack_bf16(p2, p3);
       }
 #pragma unroll
-      for (int i = 0; i < BATCH / 2; ++i) asm volatile("" ::"r"(pk[i]));
+      for (int i = 0; i < BATCH / 2; ++i) acc ^= pk[i];
     } else {
       uint32_t pk[BATCH / 2];
 #pragma unroll
@@ -102,12 +102,14 @@ __global__ void __launch_bounds__(512, 1) loop(uint32_t* out, int iters, float s
         pk[i >> 1] = e;
       }
 #pragma unroll
-      for (int i = 0; i < BATCH / 2; ++i) asm volatile("" ::"r"(pk[i]));
+      for (int i = 0; i < BATCH / 2; ++i) acc ^= pk[i];
     }
-    // keep the compiler from hoisting the batch out of the loop WITHOUT adding instructions (an earlier version perturbed the scores with
-    // three integer ops each and measured mostly its own scaffolding): the scores become opaque again through empty asm statements
+    // new "scores" for the next batch (keeps the compiler from hoisting the batch out of the loop).  CAVEAT: this perturbation costs ~3 integer
+    // instructions per score on the ALU pipe, so the absolute cycles of this benchmark include its own scaffolding (profiles/r02_softmax_loop.txt:
+    // ~11-12 clk per score row for every form); a version with empty-asm barriers instead let the compiler hoist the exponentials (65 scores/clk/SM,
+    // four times the MUFU rate) and was discarded.  Use the numbers only to compare forms with each other.
 #pragma unroll
-    for (int i = 0; i < BATCH; ++i) asm volatile("" : "+f"(v[i]));
+    for (int i = 0; i < BATCH; ++i) v[i] = __uint_as_float((__float_as_uint(v[i]) & 0xfffffff0u) | ((acc >> (i & 15)) & 3u));
   }
   const long long t1 = clock64();
   if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;

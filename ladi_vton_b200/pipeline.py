@@ -41,9 +41,9 @@ def _randn(shape, generator, device):
 
 class _Session:
     """Everything one (batch, size, conditioning layout) shape needs to be replayable: static input buffers, the persistent UNet input /
-    latents / step counter, and three captured CUDA graphs -- `pre` (mask + pose preprocessing, VAE encode x2, posterior samples, EMASC,
-    UNet input assembly, text K/V), `step` (UNet forward + CFG + DDIM, replayed N times) and `post` (VAE decode with the EMASC skips +
-    image conversion)."""
+    latents / step counter, and the captured CUDA graphs -- `pre` (mask + pose preprocessing, VAE encode x2, posterior samples, EMASC,
+    UNet input assembly, text K/V), `loop` (all N denoising steps; or `step`, one step replayed N times, when something has to happen on the
+    host between steps: eta > 0, cloth_cond_rate < 1, a callback) and `post` (VAE decode with the EMASC skips + image conversion)."""
 
     def __init__(self, B, Bp, h, w, H, W, in_pitch, n_pose, ctx_shape, kv_total, device):
         f32 = dict(dtype=torch.float32, device=device)
@@ -64,9 +64,9 @@ class _Session:
         self.out_f32 = self.out_u8 = None
         self.host_f32 = self.host_u8 = None  # pinned staging for the D2H of the result
         self.calls = 0
-        self.g_pre = self.g_step = self.g_post = None
-        self.step_key = self.pre_key = self.post_key = None
-        self.step_nodes = self.pre_nodes = self.post_nodes = 0
+        self.g_pre = self.g_step = self.g_post = self.g_loop = None
+        self.step_key = self.pre_key = self.post_key = self.loop_key = None
+        self.step_nodes = self.pre_nodes = self.post_nodes = self.loop_nodes = 0
 
 
 class StableDiffusionTryOnePipeline:
@@ -380,7 +380,14 @@ class StableDiffusionTryOnePipeline:
         stochastic = eta > 0
         step_graph = self.use_cuda_graph and callback is None
         step_key = self._graph_key() + (s.coef.data_ptr(), float(guidance_scale), stochastic)
-        for i in range(num_inference_steps):
+        per_step_host_work = stochastic or (lay["cloth"] and cloth_steps > 0)  # noise draw / cloth zeroing between steps
+        if step_graph and use_graph and not per_step_host_work:
+            # the common case (CLI defaults): ALL N steps as one captured graph -- one launch instead of N (the step counter lives on the device)
+            self._run(s, "loop", lambda: [self._step(s, cfg, guidance_scale) for _ in range(num_inference_steps)], step_key + (num_inference_steps,), True)
+            steps_left = range(0)
+        else:
+            steps_left = range(num_inference_steps)
+        for i in steps_left:
             if lay["cloth"] and i >= n_zero_from and cloth_steps > 0:
                 s.unet_in[..., lay["c_cloth"]:lay["c_cloth"] + 4].zero_()
             if stochastic:  # DDIMScheduler.step draws randn_tensor(model_output.shape, generator=...) once per step (after the 3 initial draws)

@@ -278,6 +278,11 @@ class StableDiffusionTryOnePipeline:
         """Run one of the three pieces eagerly (first call of a shape = warm-up, or graphs off) or as a captured graph."""
         g_attr, k_attr, n_attr = f"g_{which}", f"{which}_key", f"{which}_nodes"
         if not use_graph:
+            # an eager run re-binds the tensors the pieces hand to each other (e.g. the EMASC outputs): a graph of this piece captured earlier
+            # would keep writing its own, older buffers -- drop it so that the next graphed call re-captures
+            if which != "step":
+                setattr(s, g_attr, None)
+                setattr(s, k_attr, None)
             return fn()
         if getattr(s, g_attr) is None or getattr(s, k_attr) != key:
             g = torch.cuda.CUDAGraph()

@@ -297,9 +297,16 @@ class AutoencoderKL:
         if self._use_engine():  # one ABI call (csrc/engine.cu vae_decode)
             img = torch.empty((B, 8 * h, 8 * w, 4), dtype=torch.float32, device=self.device)
             fl = list(feats) if feats else []
-            for t in fl:
+            lay = [int(i) for i in (int_layers or [])][:len(fl)]
+            if fl and len(lay) != len(fl):
+                raise ValueError("`int_layers` must name the encoder layer of every intermediate feature")
+            want_c = {0: cfg.out_channels, 1: ch[0], 2: ch[1], 3: ch[2], 4: ch[3], 5: ch[3]}  # EMASC output widths per encoder layer (hubconf.py:41-42)
+            want_f = {0: 1, 1: 1, 2: 1, 3: 2, 4: 4, 5: 8}
+            for t, i in zip(fl, lay):
+                if i not in want_c or tuple(t.shape) != (B, 8 * h // want_f[i], 8 * w // want_f[i], want_c[i]):
+                    raise ValueError(f"intermediate feature of layer {i}: expected NHWC {(B, 8 * h // want_f.get(i, 1), 8 * w // want_f.get(i, 1), want_c.get(i))}, got {tuple(t.shape)}")
                 assert t.dtype == torch.bfloat16 and t.stride(3) == 1 and t.stride(2) == (t.shape[3] + 7) // 8 * 8, "EMASC features: dense NHWC bf16 (pitch = channels rounded up to 8)"
-            layers = (C.c_int * max(1, len(fl)))(*[int(i) for i in (int_layers or [])][:len(fl)])
+            layers = (C.c_int * max(1, len(fl)))(*lay)
             ws = self.engine.workspace(eng.MODULE_VAE_DECODE, B, h, w)
             lib.call("ladi_vae_decode_emasc", self.engine.h, ops._ptr(zin), B, h, w, eng.ptr_array(fl, max(1, len(fl))), len(fl), layers, ops._ptr(img),
                      ops._ptr(ws), ws.numel(), ops._stream())

@@ -190,6 +190,10 @@ LADI_API int ladi_image_out(const void* x, int x_is_fp32, int n, int h, int w, i
 /* The same clamp followed by numpy_to_pil's (x * 255).round().astype(uint8) (DiffusionPipeline.numpy_to_pil, called at
  * tryon_pipe.py:760; round-half-to-even like numpy): NHWC uint8 [n,h,w,3], so output_type="pil" moves a quarter of the bytes to the host. */
 LADI_API int ladi_image_out_u8(const void* x, int x_is_fp32, int n, int h, int w, int x_pitch, unsigned char* out, void* stream);
+/* Sinusoidal timestep embedding of the UNet (diffusers get_timestep_embedding, flip_sin_to_cos, the input of time_embedding.linear_1)
+ * for n timesteps (device fp32 [n]), written as a (hi, lo) pair of bf16 column blocks: out bf16 [n, 2*k_pad], hi at columns [0, channels),
+ * lo = bf16(e - hi) at [k_pad, k_pad + channels), zeros elsewhere (k_pad = channels rounded up to 64: the K layout of the packed [W | W] weight). */
+LADI_API int ladi_timestep_embedding(const float* timesteps, int n, int channels, int k_pad, void* out, void* stream);
 /* ---- dataset tensorisation edge: src/utils/posemap.py:6-35 kpoint_to_heatmap for n_maps key-points
  * (keypoints fp32 [n_maps,2] = (x, y) in pixels; the reference calls it per sample and joint with sigma 9, src/dataset/vitonhd.py:277-287):
  * out fp32 [n_maps,h,w] = exp(-|p - k|^2 / sigma^2) / (max + eps), all zeros for a key-point with no coordinate > 0. */
@@ -306,6 +310,7 @@ LADI_API int ladi_engine_query(const ladi_engine* engine, int what);
 #define LADI_MODULE_VAE_DECODE 2  /* (batch, latent h, latent w) */
 #define LADI_MODULE_EMASC 3       /* (batch, image height, image width) */
 #define LADI_MODULE_ADAPTER 4     /* (batch, height = tokens, width ignored) */
+#define LADI_MODULE_UNET_PLAN 5   /* ladi_unet_plan_steps: (batch = number of timesteps, height / width ignored) */
 /* bytes of caller workspace one call of `module` needs at this shape (a walk of the module body with the allocator only); -1 on error */
 LADI_API int64_t ladi_workspace_bytes(ladi_engine* engine, int module, int batch, int height, int width);
 /* the launch sequence of the last ladi_workspace_bytes walk, one op per line (tooling / the CPU test that pins it to the Python sequencing) */
@@ -318,6 +323,12 @@ LADI_API const char* ladi_engine_trace(const ladi_engine* engine);
  * eps_out NHWC fp32 [batch, h, w, 4]. */
 LADI_API int ladi_unet_forward(ladi_engine* engine, const void* x_in, const int* step_ptr, const float* steps, const void* ctx_kv, int batch, int lat_h,
                                int lat_w, int ctx_tokens, void* eps_out, void* workspace, int64_t workspace_bytes, void* stream);
+/* The two step-invariant tables ladi_unet_forward reads (the reference recomputes both inside every forward, tryon_pipe.py:732):
+ *   steps  fp32 [n][temb_total] = conv1.bias + time_emb_proj(silu(time_embedding(t_s))) for every resnet, from the n timesteps (device fp32 [n],
+ *          the scheduler's `timesteps`, tryon_pipe.py:650-651); needs ladi_workspace_bytes(engine, LADI_MODULE_UNET_PLAN, n, 0, 0) of workspace;
+ *   ctx_kv bf16 [rows = batch * ctx_tokens][kv_total] = the text context (bf16 [rows][ctx_dim]) through every cross-attention layer's to_k / to_v. */
+LADI_API int ladi_unet_plan_steps(ladi_engine* engine, const float* timesteps, int n, float* steps_out, void* workspace, int64_t workspace_bytes, void* stream);
+LADI_API int ladi_unet_plan_context(ladi_engine* engine, const void* ctx, int rows, int ctx_dim, void* ctx_kv_out, void* stream);
 /* x NHWC bf16 [batch, H, W, 8] (3 valid channels) -> posterior moments NHWC fp32 [batch, H/8, W/8, 2*latent] (quant_conv folded in) and the
  * retained encoder features (vae.py:100-109): skips[1] (= skips[2]) [batch,H,W,C0], skips[3] [batch,H/2,W/2,C0], skips[4] [.., /4, C1],
  * skips[5] [.., /8, C2]; skips[0] is unused (the input itself); a null entry (or skips == NULL) keeps that feature in the workspace. */

@@ -471,6 +471,31 @@ void unet_forward(Ctx& c, const T& x_in, const int* step_ptr, const float* steps
   c.drop(hn);
 }
 
+// plan_steps (unet.py): sinusoid (hi, lo) table -> linear_1 + SiLU -> linear_2 + SiLU (= silu(emb)) -> all time_emb_proj at once (+ conv1.bias), fp32 out
+void unet_plan_steps(Ctx& c, const float* timesteps, int n, const T& steps_out) {
+  const Weight& w1 = c.W("te1.w");
+  if (!c.ok()) return;
+  const int kp = w1.cols / 2, c0 = c.e->cfg.unet_channels[0];
+  T pair = c.make(1, 1, n, 2 * kp);
+  c.rec("timestep_embedding t=@%llx n=%d c=%d kp=%d out=@%llx", Ctx::A(timesteps), n, c0, kp, Ctx::A(pair.p));
+  if (!c.plan && c.ok()) {
+    const int r = ladi_timestep_embedding(timesteps, n, c0, kp, pair.p, c.st);
+    if (r != LADI_OK) c.rc = r;
+  }
+  ConvOpt o1;
+  o1.bias = c.F("te1.b"); o1.act = LADI_ACT_SILU;
+  T e1 = c.gemm(pair, w1, w1.rows, o1);
+  c.drop(pair);
+  ConvOpt o2;
+  o2.bias = c.F("te2.b"); o2.act = LADI_ACT_SILU;
+  T e2 = c.gemm(e1, c.W("te2.w"), c.W("te2.w").rows, o2);
+  c.drop(e1);
+  ConvOpt o3;
+  o3.bias = c.F("temb_all.b"); o3.out_fp32 = true; o3.out = &steps_out;
+  c.gemm(e2, c.W("temb_all.w"), c.e->temb_total, o3);
+  c.drop(e2);
+}
+
 // =================================================================================================================== VAE
 T vae_resnet(Ctx& c, const std::string& p, const T& x, int co) {
   T hn = c.groupnorm(&x, nullptr, p + ".norm1", 1e-6f, true);
@@ -821,6 +846,34 @@ extern "C" int ladi_unet_forward(ladi_engine* h, const void* x_in, const int* st
   return run_unet(h, false, nullptr, x_in, step_ptr, steps, ctx_kv, batch, lat_h, lat_w, ctx_tokens, eps_out, workspace, (size_t)workspace_bytes, stream, nullptr);
 }
 
+static int run_plan_steps(ladi_engine* h, bool plan, std::string* trace, const float* timesteps, int n, void* steps_out, void* ws, size_t ws_bytes, void* stream,
+                          size_t* high) {
+  Call k(&h->e, ws, ws_bytes, stream, plan);
+  k.c.trace = trace;
+  const T out = view(steps_out, 1, 1, n, h->e.temb_total, h->e.temb_total, true);
+  unet_plan_steps(k.c, timesteps, n, out);
+  if (high) *high = k.c.arena.high;
+  return k.c.rc;
+}
+
+extern "C" int ladi_unet_plan_steps(ladi_engine* h, const float* timesteps, int n, float* steps_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  ENGINE_CHECK(h);
+  LADI_CHECK(timesteps && steps_out && workspace && n > 0, "unet_plan_steps: bad arguments");
+  return run_plan_steps(h, false, nullptr, timesteps, n, steps_out, workspace, (size_t)workspace_bytes, stream, nullptr);
+}
+
+extern "C" int ladi_unet_plan_context(ladi_engine* h, const void* ctx, int rows, int ctx_dim, void* ctx_kv_out, void* stream) {
+  ENGINE_CHECK(h);
+  LADI_CHECK(ctx && ctx_kv_out && rows > 0 && ctx_dim > 0 && ctx_dim % 8 == 0, "unet_plan_context: bad arguments");
+  Call k(&h->e, nullptr, 0, stream, false);
+  const T c = view(ctx, 1, 1, rows, ctx_dim, ctx_dim);
+  const T out = view(ctx_kv_out, 1, 1, rows, h->e.kv_total, h->e.kv_total);
+  ConvOpt o;
+  o.out = &out;
+  k.c.gemm(c, k.c.W("kv_all.w"), h->e.kv_total, o);
+  return k.c.rc;
+}
+
 static int run_encode(ladi_engine* h, bool plan, std::string* trace, const void* x, int B, int H, int W, void* moments, void* const* skips, void* ws, size_t ws_bytes,
                       void* stream, size_t* high) {
   Call k(&h->e, ws, ws_bytes, stream, plan);
@@ -963,6 +1016,9 @@ extern "C" int64_t ladi_workspace_bytes(ladi_engine* h, int module, int batch, i
       break;
     case LADI_MODULE_ADAPTER:
       rc = run_adapter(h, true, &h->e.trace, X, batch, height /* tokens */, Y, nullptr, 0, nullptr, &high);
+      break;
+    case LADI_MODULE_UNET_PLAN:
+      rc = run_plan_steps(h, true, &h->e.trace, reinterpret_cast<const float*>(X), batch, Y, nullptr, 0, nullptr, &high);
       break;
     default:
       ladi_set_error("workspace_bytes: unknown module %d", module);

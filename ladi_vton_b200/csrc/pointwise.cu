@@ -596,6 +596,26 @@ __global__ void pose_heatmap_kernel(const float* __restrict__ kpts, int n_maps, 
   }
 }
 
+// diffusers get_timestep_embedding(flip_sin_to_cos=True, downscale_freq_shift=0) -- the input of UNet2DConditionModel.time_embedding:
+// emb[s, :] = [cos(t_s * f_i), sin(t_s * f_i)], f_i = exp(-ln(10000) * i / half).  Written as a (hi, lo) pair of bf16 columns (hi = bf16(e), lo = bf16(e - hi)) so
+// the first linear of the time MLP reads it through the bf16 GEMM with 2^-17 input error: out [n, 2 * kp], hi at [0, c0), lo at [kp, kp + c0), zeros elsewhere.
+__global__ void timestep_embed_kernel(const float* __restrict__ timesteps, int n, int c0, int kp, bf16* __restrict__ out) {
+  ptx::pdl_wait();
+  const int half = c0 / 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * kp; i += gridDim.x * blockDim.x) {
+    const int s = i / kp, j = i - s * kp;
+    float e = 0.f;
+    if (j < c0) {
+      const int k = j < half ? j : j - half;
+      const float arg = timesteps[s] * expf(-9.210340371976184f * (float)k / (float)half);
+      e = j < half ? cosf(arg) : sinf(arg);
+    }
+    const bf16 hi = __float2bfloat16(e);
+    out[(size_t)s * 2 * kp + j] = hi;
+    out[(size_t)s * 2 * kp + kp + j] = __float2bfloat16(e - __bfloat162float(hi));
+  }
+}
+
 inline int grid_for(int64_t total, int block = 256) {
   int64_t g = (total + block - 1) / block;
   const int64_t cap = (int64_t)ladi_num_sms() * 16;
@@ -761,5 +781,11 @@ extern "C" int ladi_pose_heatmaps(const float* keypoints, int n_maps, int h, int
 
 extern "C" int ladi_image_out(const void* x, int x_is_fp32, int n, int h, int w, int x_pitch, float* out, void* stream) {
   LADI_CUDA(ladi_launch(image_out_kernel, dim3(grid_for((int64_t)n * h * w * 3)), dim3(256), 0, STREAM, x, x_is_fp32, (int64_t)n * h * w, x_pitch, out));
+  return LADI_OK;
+}
+
+extern "C" int ladi_timestep_embedding(const float* timesteps, int n, int channels, int k_pad, void* out, void* stream) {
+  LADI_CHECK(timesteps && out && n > 0 && channels > 0 && channels % 2 == 0 && k_pad >= channels && k_pad % 8 == 0, "timestep_embedding: bad arguments");
+  LADI_CUDA(ladi_launch(timestep_embed_kernel, dim3(grid_for((int64_t)n * k_pad)), dim3(256), 0, STREAM, timesteps, n, channels, k_pad, (bf16*)out));
   return LADI_OK;
 }

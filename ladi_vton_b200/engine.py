@@ -12,7 +12,7 @@ import torch
 
 from . import lib
 
-MODULE_UNET, MODULE_VAE_ENCODE, MODULE_VAE_DECODE, MODULE_EMASC, MODULE_ADAPTER = 0, 1, 2, 3, 4
+MODULE_UNET, MODULE_VAE_ENCODE, MODULE_VAE_DECODE, MODULE_EMASC, MODULE_ADAPTER, MODULE_UNET_PLAN = 0, 1, 2, 3, 4, 5
 Q_TEMB_TOTAL, Q_KV_TOTAL, Q_IN_PITCH = 0, 1, 2
 
 

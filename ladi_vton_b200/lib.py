@@ -104,6 +104,9 @@ SIGNATURES = {
     "ladi_workspace_bytes": ([_P, _I, _I, _I, _I], _L),
     "ladi_engine_trace": ([_P], C.c_char_p),
     "ladi_unet_forward": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _L, _P], _I),
+    "ladi_unet_plan_steps": ([_P, _P, _I, _P, _P, _L, _P], _I),
+    "ladi_unet_plan_context": ([_P, _P, _I, _I, _P, _P], _I),
+    "ladi_timestep_embedding": ([_P, _I, _I, _I, _P, _P], _I),
     "ladi_vae_encode": ([_P, _P, _I, _I, _I, _P, _PP, _P, _L, _P], _I),
     "ladi_vae_decode_emasc": ([_P, _P, _I, _I, _I, _PP, _I, C.POINTER(C.c_int), _P, _P, _L, _P], _I),
     "ladi_emasc_forward": ([_P, _PP, _PP, _I, _I, _I, _PP, _P, _L, _P], _I),

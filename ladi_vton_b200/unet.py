@@ -304,6 +304,16 @@ class UNet2DConditionModel:
         key = tuple(int(x) for x in timesteps)
         if self._steps is not None and self._steps_key == key:
             return self._steps  # same schedule as the previous call: the table (and its address) stands
+        keep = self._steps if (self._steps is not None and tuple(self._steps.shape) == (len(timesteps), self.temb_total)) else None
+        if getattr(self, "engine", None) is not None and ops.PROFILE is None and lib.RECORD is None:
+            # one ABI call (csrc/engine.cu unet_plan_steps): sinusoid table on the device, the time MLP and all 22 time_emb_proj as three GEMMs
+            n = len(timesteps)
+            tdev = torch.tensor([float(x) for x in timesteps], dtype=torch.float32).to(self.device)
+            out = keep if keep is not None else torch.empty((n, self.temb_total), dtype=torch.float32, device=self.device)
+            ws = self.engine.workspace(eng.MODULE_UNET_PLAN, n, 0, 0)
+            lib.call("ladi_unet_plan_steps", self.engine.h, ops._ptr(tdev), n, ops._ptr(out), ops._ptr(ws), ws.numel(), ops._stream())
+            self._steps, self._steps_key = out, key
+            return self._steps
         half = c0 // 2
         t = torch.tensor([float(x) for x in timesteps], dtype=torch.float32)
         freq = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
@@ -316,7 +326,6 @@ class UNet2DConditionModel:
         pair[:, :c0], pair[:, kp:kp + c0] = hi, lo
         e1 = ops.gemm(pair.to(self.device), P["te1.w"], P["te1.w"].shape[0], bias=P["te1.b"], act=ops.ACT_SILU)
         e2 = ops.gemm(e1, P["te2.w"], P["te2.w"].shape[0], bias=P["te2.b"], act=ops.ACT_SILU)  # = silu(emb)
-        keep = self._steps if (self._steps is not None and tuple(self._steps.shape) == (len(timesteps), self.temb_total)) else None
         self._steps = ops.gemm(e2, P["temb_all.w"], self.temb_total, bias=P["temb_all.b"], out_fp32=True, out=keep)  # stable address
         self._steps_key = key
         return self._steps
@@ -328,6 +337,13 @@ class UNet2DConditionModel:
         c = ctx.to(self.device, torch.bfloat16).contiguous().view(B * T, D)
         if out is None and self._ctx is not None and tuple(self._ctx.shape) == (B, T, self.kv_total):
             out = self._ctx
+        if getattr(self, "engine", None) is not None and ops.PROFILE is None and lib.RECORD is None and D % 8 == 0:
+            if out is None:
+                out = torch.empty((B, T, self.kv_total), dtype=torch.bfloat16, device=self.device)
+            assert out.is_contiguous()
+            lib.call("ladi_unet_plan_context", self.engine.h, ops._ptr(c), B * T, D, ops._ptr(out), ops._stream())  # one GEMM, csrc/engine.cu
+            self._ctx = out.view(B, T, self.kv_total)
+            return self._ctx
         kv = ops.gemm(c, self.P["kv_all.w"], self.kv_total, out=None if out is None else out.view(B * T, self.kv_total))
         self._ctx = kv.view(B, T, self.kv_total)
         return self._ctx

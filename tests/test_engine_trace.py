@@ -153,6 +153,12 @@ def test_unet_sequence_matches_python(record, monkeypatch, B, h, w, fuse):
     n = compare(record.RECORD, e.trace(eng.MODULE_UNET, B, h, w), "UNet forward")
     assert n > 300
     assert e.workspace_bytes(eng.MODULE_UNET, B, h, w) > 0
+    # the step-invariant table: sinusoid (device kernel in C++, host trig in the Python sequencing) -> time MLP -> all time_emb_proj: the three GEMMs must match
+    record.RECORD.clear()
+    unet._steps = unet._steps_key = None
+    unet.plan_steps([981, 961, 941])
+    cpp = "\n".join(l for l in e.trace(eng.MODULE_UNET_PLAN, 3, 0, 0).splitlines() if not l.startswith("timestep_embedding"))
+    assert compare(record.RECORD, cpp, "UNet plan_steps") == 3
 
 
 @pytest.mark.parametrize("fuse", ["1", "0"])

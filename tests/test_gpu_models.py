@@ -477,8 +477,19 @@ def test_engine_abi_unet_forward_and_denoise_loop(cuda):
     g = torch.Generator().manual_seed(0)
     x = torch.randn((2 * B, 31, h, w), generator=g)
     ctx = torch.randn((2 * B, 77, 128), generator=g)
+    steps = unet.plan_steps([801, 601, 401])      # ladi_unet_plan_steps (sinusoid table on the device)
+    kv = unet.plan_context(ctx.to(cuda))          # ladi_unet_plan_context
+    ops.PROFILE = []  # the Python sequencing of the same tables (host trigonometry): equal up to the fp32 ulps of cosf / sinf
+    try:
+        unet._steps = unet._steps_key = None
+        steps_py = unet.plan_steps([801, 601, 401]).clone()
+        kv_py = unet.plan_context(ctx.to(cuda), out=torch.empty_like(kv)).clone()
+    finally:
+        ops.PROFILE = None
+    unet._steps = unet._steps_key = None
     steps = unet.plan_steps([801, 601, 401])
-    kv = unet.plan_context(ctx.to(cuda))
+    assert torch.equal(kv, kv_py)
+    assert (steps - steps_py).abs().max() <= 1e-3 * steps_py.abs().max()
     xin = torch.zeros((2 * B, h, w, unet.in_pitch), dtype=torch.bfloat16, device=cuda)
     ops.nchw_to_nhwc(x.to(cuda), xin)
     step = torch.tensor([1, 0], dtype=torch.int32, device=cuda)

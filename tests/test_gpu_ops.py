@@ -555,3 +555,21 @@ def test_pair_mode_errors(cuda):
     w = weights.pack_linear(rnd((128, 64), cuda, 2))
     with pytest.raises(RuntimeError, match="pair_mode=1"):
         ops.gemm(a, w, 128, force_bn=128, pair=True)
+
+
+def test_timestep_embedding(cuda):
+    """diffusers get_timestep_embedding (flip_sin_to_cos=True, downscale_freq_shift=0) as a (hi, lo) pair of bf16 column blocks."""
+    import ctypes as C
+    import math
+    from ladi_vton_b200 import lib
+    c0, kp = 320, 320
+    t = torch.tensor([981.0, 501.0, 21.0, 1.0], device=cuda)
+    out = torch.full((4, 2 * kp), 7.0, dtype=torch.bfloat16, device=cuda)
+    lib.call("ladi_timestep_embedding", C.c_void_p(t.data_ptr()), 4, c0, kp, C.c_void_p(out.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    half = c0 // 2
+    freq = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    arg = t.cpu()[:, None] * freq[None, :]
+    ref = torch.cat([torch.cos(arg), torch.sin(arg)], dim=-1)
+    got = out[:, :c0].float().cpu() + out[:, kp:kp + c0].float().cpu()
+    assert (got - ref).abs().max() < 2e-5  # hi + lo carries ~17 bits

@@ -572,4 +572,8 @@ def test_timestep_embedding(cuda):
     arg = t.cpu()[:, None] * freq[None, :]
     ref = torch.cat([torch.cos(arg), torch.sin(arg)], dim=-1)
     got = out[:, :c0].float().cpu() + out[:, kp:kp + c0].float().cpu()
-    assert (got - ref).abs().max() < 2e-5  # hi + lo carries ~17 bits
+    # hi + lo carries ~17 bits; the dominant term is one fp32 ulp of the frequency (device expf vs torch.exp) times t <= 1000: ~6e-5 at the first columns
+    assert (got - ref).abs().max() < 2e-4
+    arg_dev = t.cpu()[:, None] * torch.exp((-math.log(10000.0) * torch.arange(half, dtype=torch.float64) / half)).float()[None, :]
+    assert (got[:, half:] - torch.sin(arg_dev.double()).float()).abs().max() < 2e-4
+    assert float(out[:, c0:kp].abs().max() if kp > c0 else 0.0) == 0.0

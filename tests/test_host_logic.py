@@ -93,6 +93,52 @@ def test_pack_conv_shortcut_and_geglu_and_linear():
     assert weights.pack_linear(torch.ones(5, 70)).shape == (5, 128)
 
 
+def test_pack_conv_up2x_matches_upsample_then_conv():
+    """weights.pack_conv_up2x (sub-pixel form of diffusers Upsample2D: nearest-2x + conv3x3) walked like ladi_conv2d_bf16's up2x mode does --
+    per output parity (py, px): 4 taps (ty, tx) reading input pixel (i + py - 1 + ty, j + px - 1 + tx), K order = taps row-major x 64-channel blocks,
+    weight rows [parity * c_out, (parity + 1) * c_out) -- against F.conv2d(F.interpolate(x, 2, 'nearest'))."""
+    from ladi_vton_b200 import weights
+    g = torch.Generator().manual_seed(2)
+    ci, co, h, w = 96, 40, 6, 5
+    x = torch.randn(2, ci, h, w, generator=g)
+    wt = torch.randn(co, ci, 3, 3, generator=g)
+    packed = weights.pack_conv_up2x(wt, [ci]).float()
+    cp = (ci + 63) // 64 * 64
+    assert packed.shape == (4 * co, 4 * cp)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), wt, padding=1)
+    out = torch.zeros_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1, 0, cp - ci))  # zero padding = TMA out-of-bounds fill; channel padding = zero weights
+    for par in range(4):
+        py, px = par >> 1, par & 1
+        cols = [xp[:, :, py + ty: py + ty + h, px + tx: px + tx + w] for ty in (0, 1) for tx in (0, 1)]
+        a = torch.cat(cols, dim=1).permute(0, 2, 3, 1).reshape(-1, 4 * cp)
+        y = (a @ packed[par * co:(par + 1) * co].t()).reshape(2, h, w, co).permute(0, 3, 1, 2)
+        out[:, :, py::2, px::2] = y
+    assert (out - ref).abs().max() < 1e-2 * ref.abs().max()  # bf16 rounding of the merged weights
+    # the merge itself is exact in fp32
+    m = weights.merge_up2x(wt)
+    assert torch.allclose(m.sum(dim=(0, 3, 4)) / 4, wt.sum(dim=(2, 3)), atol=1e-4)
+
+
+def test_fold_layernorm_algebra():
+    """LN(x) W^T + b == rstd * (x W'^T - mean * colsum(W')) + (W beta + b) with W' = W diag(gamma) (weights.fold_layernorm), per-row statistics from
+    per-32-column {sum, sum of squares} partials as the producer GEMM's epilogue writes them."""
+    from ladi_vton_b200 import weights
+    g = torch.Generator().manual_seed(3)
+    C, N, M = 320, 96, 50
+    x = torch.randn(M, C, generator=g) * 2 + 0.5
+    W, b = torch.randn(N, C, generator=g) * C ** -0.5, torch.randn(N, generator=g)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    wp, cs, bp = weights.fold_layernorm(W, gamma, beta, b)
+    parts = x.view(M, C // 32, 32)
+    s, q = parts.sum(-1).sum(-1), (parts * parts).sum(-1).sum(-1)
+    mean = s / C
+    rstd = torch.rsqrt((q / C - mean * mean).clamp_min(0) + 1e-5)
+    got = rstd[:, None] * (x @ wp.float().t() - mean[:, None] * cs[None, :]) + bp
+    ref = F.layer_norm(x, (C,), gamma, beta, 1e-5) @ W.t() + b
+    assert (got - ref).abs().max() < 2e-2 * ref.abs().max()  # bf16 rounding of W'
+
+
 def test_pipeline_host_validation_and_signature():
     import inspect
     import ladi_vton_b200 as L

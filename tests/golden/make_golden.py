@@ -1,4 +1,4 @@
-"""Generates tests/golden/tryon_small.npz by running the REFERENCE'S OWN FILES -- /root/reference/src/vto_pipelines/
+"""Generates tests/golden/tryon_small.npz (and tryon_small_branches.npz: eta > 0, generator lists) by running the REFERENCE'S OWN FILES -- /root/reference/src/vto_pipelines/
 tryon_pipe.py, src/models/AutoencoderKL.py, src/models/vae.py, src/models/emasc.py, src/utils/data_utils.py, imported
 unmodified -- on the diffusers shim (oracle/shim), CPU fp32, with the seeded small-config weights and synthetic inputs
 that the tests rebuild.  Run in the build container only (needs /root/reference):
@@ -59,6 +59,22 @@ def main():
         out["emasc2_sub"] = emasc([f.clone() for f in feats[1:6]])[2][:, ::8, ::4, ::4].contiguous().numpy()
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "tryon_small.npz"), **out)
     print({k: (v.shape, float(np.abs(v).mean())) for k, v in out.items()})
+    # ---- the less-travelled branches of the reference `__call__` (round 2): stochastic DDIM (`eta` > 0: tryon_pipe.py:337-345,740) and a LIST of
+    # per-sample generators (prepare_latents :412-416, prepare_mask_latents :445-450 -- with EMASC that branch of the reference indexes the per-sample
+    # list with the layer indices (:452-456) and cannot run, so the list cases use emasc=None, where the decode takes no intermediate features)
+    br = {}
+    cases = (("eta_cfg", 0.6, False, True), ("list_noemasc", 0.0, True, False), ("list_eta_noemasc", 0.6, True, False))
+    for tag, eta, as_list, with_emasc in cases:
+        inp = S.synthetic_inputs(2, 128, 64, seed=1234, ctx_dim=128)
+        pipe = StableDiffusionTryOnePipeline(vae=vae, text_encoder=_TE(), tokenizer=None, unet=unet, scheduler=DDIMScheduler(),
+                                             emasc=emasc if with_emasc else None, emasc_int_layers=[1, 2, 3, 4, 5] if with_emasc else None)
+        gen = [torch.Generator().manual_seed(5), torch.Generator().manual_seed(6)] if as_list else torch.Generator().manual_seed(7)
+        img = pipe(image=inp["image"], mask_image=inp["mask_image"], pose_map=inp["pose_map"], warped_cloth=inp["warped_cloth"],
+                   prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"], height=128, width=64,
+                   num_inference_steps=3, guidance_scale=7.5, eta=eta, generator=gen, output_type="np").images
+        br[f"image_{tag}"] = img.astype(np.float32)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "tryon_small_branches.npz"), **br)
+    print({k: (v.shape, float(np.abs(v).mean())) for k, v in br.items()})
 
 
 if __name__ == "__main__":

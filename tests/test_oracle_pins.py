@@ -110,6 +110,25 @@ def test_oracle_reproduces_reference_golden(tag, gs):
     assert np.abs(img - gold[f"image_{tag}"]).max() < 1e-4
 
 
+@pytest.mark.parametrize("tag,eta,as_list,with_emasc", [("eta_cfg", 0.6, False, True), ("list_noemasc", 0.0, True, False), ("list_eta_noemasc", 0.6, True, False)])
+def test_oracle_reproduces_reference_golden_branches(tag, eta, as_list, with_emasc):
+    """tests/golden/tryon_small_branches.npz: the REFERENCE'S OWN tryon_pipe.py run (make_golden.py) with stochastic DDIM (`eta` > 0) and with a list
+    of per-sample generators (with emasc=None: the reference's list branch cannot run with EMASC, tryon_pipe.py:452-456) -- the restated oracle, which
+    the GPU tests of these branches compare the engine with, must reproduce it."""
+    from ladi_oracle.parts import DDIMScheduler
+    from ladi_oracle.pipeline import OracleTryOnPipeline
+    from ladi_vton_b200 import synthetic as S
+    gold = np.load(os.path.join(os.path.dirname(GOLD), "tryon_small_branches.npz"))
+    full, ov, oe = _oracle_small()
+    pipe = full if with_emasc else OracleTryOnPipeline(ov, full.unet, DDIMScheduler(), None, None)
+    inp = S.synthetic_inputs(2, 128, 64, seed=1234, ctx_dim=128)
+    gen = [torch.Generator().manual_seed(5), torch.Generator().manual_seed(6)] if as_list else torch.Generator().manual_seed(7)
+    img = pipe(inp["image"], inp["mask_image"], inp["pose_map"], inp["warped_cloth"], inp["prompt_embeds"], inp["negative_prompt_embeds"],
+               height=128, width=64, num_inference_steps=3, guidance_scale=7.5, generator=gen, eta=eta)
+    assert img.shape == gold[f"image_{tag}"].shape
+    assert np.abs(img - gold[f"image_{tag}"]).max() < 1e-4
+
+
 def test_oracle_vae_emasc_golden():
     from ladi_vton_b200 import synthetic as S
     gold = np.load(GOLD)

@@ -73,6 +73,30 @@ def main():
                    prompt_embeds=inp["prompt_embeds"], negative_prompt_embeds=inp["negative_prompt_embeds"], height=128, width=64,
                    num_inference_steps=3, guidance_scale=7.5, eta=eta, generator=gen, output_type="np").images
         br[f"image_{tag}"] = img.astype(np.float32)
+    # ---- component level, reference classes only: (a) the train_emasc.py:388-403 forward (posterior of the image, skips of the masked image, EMASC,
+    # mask_features, decode of the posterior SAMPLE); (b) decode with int_layers containing 0 and 1 (src/models/vae.py:204-210), six-scale EMASC
+    from src.utils.data_utils import mask_features  # noqa: E402  (reference file)
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(11)
+        image = torch.rand((2, 3, 128, 64), generator=g) * 2 - 1
+        mask = torch.zeros((2, 1, 128, 64)); mask[:, :, 30:100, 10:50] = 1
+        int_layers = [1, 2, 3, 4, 5]
+        posterior_im, _ = vae.encode(image)
+        _, feats = vae.encode(image * (1 - mask))
+        proc = mask_features(emasc([feats[i] for i in int_layers]), mask)
+        torch.manual_seed(3)  # the reference samples from the global RNG here (train_emasc.py:400: latent_dist.sample() without a generator)
+        lat = posterior_im.latent_dist.sample()
+        rec = vae.decode(z=lat, intermediate_features=proc, int_layers=int_layers).sample
+        br["train_emasc_latents"], br["train_emasc_rec"] = lat.numpy(), rec.numpy()
+        ein, eout = S.emasc_channels(vch)
+        em6 = RefEMASC([3] + ein, [3] + eout).eval()
+        em6.load_state_dict(S.random_state_dict(S.emasc_param_shapes([3] + ein, [3] + eout), 77))
+        x = torch.rand((2, 3, 128, 64), generator=torch.Generator().manual_seed(2)) * 2 - 1
+        z = torch.randn((2, 4, 16, 8), generator=torch.Generator().manual_seed(21))
+        layers = [0, 1, 2, 3, 4, 5]
+        _, f6 = vae.encode(x)
+        inter6 = mask_features(em6([f6[i] for i in layers]), mask)
+        br["decode_layers0"] = vae.decode(z, list(inter6), layers).sample.numpy()
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "tryon_small_branches.npz"), **br)
     print({k: (v.shape, float(np.abs(v).mean())) for k, v in br.items()})
 

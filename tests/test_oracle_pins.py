@@ -129,6 +129,39 @@ def test_oracle_reproduces_reference_golden_branches(tag, eta, as_list, with_ema
     assert np.abs(img - gold[f"image_{tag}"]).max() < 1e-4
 
 
+def test_oracle_train_emasc_forward_and_int_layers0_golden():
+    """Component-level vectors written by the reference's own classes (make_golden.py): the train_emasc.py:388-403 forward and the decode with
+    int_layers containing 0 and 1 (src/models/vae.py:204-210) -- the oracle modules the GPU tests `test_train_emasc_forward_small` and
+    `test_vae_decode_int_layers_with_0` use as their reference must reproduce them."""
+    from ladi_oracle.parts import EMASC as OE, mask_features
+    from ladi_vton_b200 import synthetic as S
+    gold = np.load(os.path.join(os.path.dirname(GOLD), "tryon_small_branches.npz"))
+    _, ov, oe = _oracle_small()
+    with torch.no_grad():
+        g = torch.Generator().manual_seed(11)
+        image = torch.rand((2, 3, 128, 64), generator=g) * 2 - 1
+        mask = torch.zeros((2, 1, 128, 64)); mask[:, :, 30:100, 10:50] = 1
+        layers = [1, 2, 3, 4, 5]
+        post, _ = ov.encode(image)
+        _, feats = ov.encode(image * (1 - mask))
+        proc = mask_features(oe([feats[i] for i in layers]), mask)
+        torch.manual_seed(3)
+        lat = post.latent_dist.sample()
+        assert np.abs(lat.numpy() - gold["train_emasc_latents"]).max() < 1e-5
+        rec = ov.decode(z=lat, intermediate_features=list(proc), int_layers=layers).sample
+        assert np.abs(rec.numpy() - gold["train_emasc_rec"]).max() < 1e-4
+        ein, eout = S.emasc_channels(S.SMALL_VAE["block_out_channels"])
+        em6 = OE([3] + ein, [3] + eout).eval()
+        em6.load_state_dict(S.random_state_dict(S.emasc_param_shapes([3] + ein, [3] + eout), 77))
+        x = torch.rand((2, 3, 128, 64), generator=torch.Generator().manual_seed(2)) * 2 - 1
+        z = torch.randn((2, 4, 16, 8), generator=torch.Generator().manual_seed(21))
+        l6 = [0, 1, 2, 3, 4, 5]
+        _, f6 = ov.encode(x)
+        inter6 = mask_features(em6([f6[i] for i in l6]), mask)
+        out = ov.decode(z, list(inter6), l6).sample
+        assert np.abs(out.numpy() - gold["decode_layers0"]).max() < 1e-4
+
+
 def test_oracle_vae_emasc_golden():
     from ladi_vton_b200 import synthetic as S
     gold = np.load(GOLD)

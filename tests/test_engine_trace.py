@@ -5,7 +5,6 @@ against the oracle.  The C++ side is walked in plan mode (no launches; `ladi_eng
 the ABI calls recorded instead of executed (`lib.RECORD`).  Addresses differ (workspace offsets vs torch allocations), so both traces
 are normalised to (buffer id, byte offset) by data flow: a buffer is born where an op writes it, reads resolve to the youngest buffer
 containing the address, external operands (weights, inputs) are numbered by first appearance."""
-import ctypes as C
 import re
 
 import pytest

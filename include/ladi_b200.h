@@ -40,6 +40,8 @@ extern "C" {
 
 LADI_API const char* ladi_last_error(void);
 LADI_API int ladi_abi_version(void);
+/* number of kernels this process has launched (or recorded into a CUDA graph under capture) through the library so far */
+LADI_API long long ladi_launch_count(void);
 
 /* ---- implicit-GEMM convolution / GEMM (tcgen05 + TMA) --------------------------------------------------------------
  * Replaces nn.Conv2d (3x3 s1 p1, 3x3 s2, 1x1) and nn.Linear of: diffusers ResnetBlock2D / Transformer2DModel /

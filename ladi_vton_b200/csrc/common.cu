@@ -2,6 +2,8 @@
 #include "common.h"
 
 #include <stdarg.h>
+
+#include <atomic>
 #include <stdlib.h>
 #include <string.h>
 
@@ -15,6 +17,12 @@ void ladi_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* ladi_last_error(void) { return g_err; }
+
+// kernels launched (or recorded into a CUDA graph being captured) by this process through the library, whichever entry point issued them --
+// an op-level call is 1-3 launches, ladi_unet_forward ~400.  bench.py's `gpu_launches` is a difference of this counter.
+static std::atomic<long long> g_launches{0};
+void ladi_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" long long ladi_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 extern "C" int ladi_abi_version(void) { return 2; }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -37,6 +37,7 @@ int ladi_encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const ui
                           const uint32_t* box, int swizzle_bytes = 128);
 
 int ladi_num_sms();
+void ladi_count_launch();  // every successful kernel launch of the library (ladi_launch / ladi_launch_cluster) -> ladi_launch_count()
 int ladi_pdl_enabled();  // env LADI_PDL=0 disables programmatic dependent launch (A/B timing)
 int ladi_conv_pair_default();  // 1 = CTA-pair (cta_group::2) conv kernels where they apply (default); env LADI_CONV_2CTA=0 -> single-CTA only
 
@@ -52,7 +53,9 @@ inline cudaError_t ladi_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = ladi_pdl_enabled() ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+  if (e == cudaSuccess) ladi_count_launch();
+  return e;
 }
 // Same, as thread-block clusters of `cluster_x` CTAs along x (grid.x must be a multiple of it).
 template <typename... KArgs, typename... Args>
@@ -67,6 +70,8 @@ inline cudaError_t ladi_launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = ladi_pdl_enabled() ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+  if (e == cudaSuccess) ladi_count_launch();
+  return e;
 }
 #endif

@@ -61,6 +61,7 @@ _PP = C.POINTER(C.c_void_p)
 SIGNATURES = {
     "ladi_abi_version": ([], C.c_int),
     "ladi_last_error": ([], C.c_char_p),
+    "ladi_launch_count": ([], C.c_longlong),
     "ladi_conv2d_bf16": ([C.POINTER(ConvDesc), _P], _I),
     "ladi_attention_bf16": ([C.POINTER(AttnDesc), _P], _I),
     "ladi_attention_d512_bf16": ([C.POINTER(AttnDesc), _P], _I),
@@ -117,7 +118,8 @@ SIGNATURES = {
 ABI_VERSION = 2
 _lib = None
 RECORD = None  # tests/test_engine_trace.py: a list -> call() appends (name, args) and launches nothing (CPU-side sequencing check)
-launches = 0  # number of kernel-launching ABI calls made by this process (bench.py reports it as gpu_launches)
+launches = 0  # kernels launched by this process through the library (bench.py reports differences of it as gpu_launches): every ABI call adds the
+# library's own count of the launches it made (an op-level call 1-3, ladi_unet_forward ~400); a captured graph adds its node count per replay (pipeline._run)
 
 
 def load():
@@ -145,8 +147,9 @@ def call(name, *args):
         RECORD.append((name, args))
         return 0
     lib = load()
+    before = lib.ladi_launch_count()
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {lib.ladi_last_error().decode()}")
-    launches += 1
+    launches += lib.ladi_launch_count() - before
     return rc

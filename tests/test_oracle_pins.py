@@ -75,6 +75,17 @@ def test_ddim_known_answers():
         ref = o.step(eps, t, x).prev_sample
         got = coef[i, 2] * ((x - coef[i, 1] * eps) * coef[i, 0]) + coef[i, 3] * eps
         assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6)
+    # eta > 0 (DDIMScheduler.step's variance noise): the table's sigma column and the sqrt(1 - a_prev - sigma^2) direction term, with the noise drawn
+    # the way the step draws it (one randn_tensor of the model output's shape per step, from the caller's generator)
+    for eta in (0.3, 1.0):
+        coef = e.coefficients(eta=eta)
+        assert coef.shape == (20, 8) and (coef[:, 4] > 0).all() and (coef[:, 5:] == 0).all()
+        g_ref, g_eng = torch.Generator().manual_seed(7), torch.Generator().manual_seed(7)
+        for i, t in enumerate(o.timesteps):
+            ref = o.step(eps, t, x, eta=eta, generator=g_ref).prev_sample
+            noise = torch.randn(eps.shape, generator=g_eng)
+            got = coef[i, 2] * ((x - coef[i, 1] * eps) * coef[i, 0]) + coef[i, 3] * eps + coef[i, 4] * noise  # ddim_cfg_kernel's arithmetic
+            assert torch.allclose(got, ref, rtol=1e-5, atol=2e-6), (eta, i)
 
 
 def test_timestep_embedding_layout():

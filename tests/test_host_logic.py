@@ -285,3 +285,16 @@ def test_synthetic_workload_matches_survey_spec():
     assert a["prompt_embeds"].shape == a["negative_prompt_embeds"].shape == (2, 77, 1024)
     assert abs(float(a["prompt_embeds"].std()) - 1.0) < 0.02
     assert not torch.equal(S.synthetic_inputs(2, 512, 384, seed=1)["image"], a["image"])
+
+
+def test_launch_counter_only_counts_real_launches():
+    """bench.py's gpu_launches = differences of lib.launches, which lib.call feeds from the library's own counter (ladi_launch_count: incremented
+    after every successful cudaLaunchKernelEx).  A call rejected by argument validation launches nothing and must not move either number."""
+    from ladi_vton_b200 import lib
+    l = lib.load()
+    n = l.ladi_launch_count()
+    assert n >= 0 and l.ladi_launch_count() == n
+    before = lib.launches
+    with pytest.raises(RuntimeError, match="ladi_add_bf16 failed"):
+        lib.call("ladi_add_bf16", None, None, None, 0, None)
+    assert lib.launches == before and l.ladi_launch_count() == n
